@@ -1,0 +1,214 @@
+/*
+ * kdsl.h -- C ABI of libkdsl.so: the B200-native (sm_100a) walker-batched VMC
+ * sampling engine that replaces the hot path of hz-xiaxz/KagomeDSL.jl.
+ *
+ * One handle = one GPU = `n_walkers` independent Markov chains advanced in
+ * lock step.  All pointers are HOST pointers unless stated otherwise; every
+ * entry point returns an int status (0 = KDSL_OK, < 0 = error; the message is
+ * available from kdsl_last_error()) and never throws.  The entry points are
+ * the ones the reference's Julia methods would bind with `ccall`
+ * (INTEGRATION.md shows the stubs); each cites the reference interface it
+ * replaces, paths relative to the reference repository root.
+ *
+ * Conventions shared with the reference:
+ *   - sites and orbital labels are 1-based; kappa[R] = 0 means "no particle of
+ *     this species on site R", otherwise the label l of the particle
+ *     (src/MonteCarlo.jl:17-28);
+ *   - matrices are column-major (Julia layout): U is ns x N, W is ns x N with
+ *     column l contiguous;
+ *   - the bond list is Ham.nn in the reference's order
+ *     (src/Hamiltonian.jl:370-373), pairs (i < j);
+ *   - one "sweep" is ONE proposed spin exchange per walker
+ *     (src/MonteCarlo.jl:538-607).
+ * W is real FP64 (valid for B = 0, where the mean-field Hamiltonian is real
+ * symmetric).
+ */
+#ifndef KDSL_H
+#define KDSL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kdsl_handle_s *kdsl_handle;
+
+/* status codes */
+#define KDSL_OK 0
+#define KDSL_ERR_INVALID_ARGUMENT (-1) /* ArgumentError / DimensionMismatch / BoundsError analogue */
+#define KDSL_ERR_CUDA (-2)             /* CUDA runtime failure (no device, OOM, launch error) */
+#define KDSL_ERR_SINGULAR (-3)         /* LinearAlgebra.SingularException analogue */
+#define KDSL_ERR_STATE (-4)            /* call sequence error (e.g. sweep before a configuration is set) */
+
+/* per-walker flag bits (kdsl_get_flags) */
+#define KDSL_FLAG_SINGULAR 1   /* exact-zero / non-finite pivot in the last W re-evaluation */
+#define KDSL_FLAG_NONFINITE 2  /* non-finite determinant ratio met in a proposal */
+#define KDSL_FLAG_BAD_SITE 4   /* Sz ArgumentError analogue (site empty or doubly occupied) in measure */
+
+/* indices into the double[KDSL_N_ACC] vector of kdsl_accumulators */
+#define KDSL_ACC_WALKER_SWEEPS 0 /* number of Carlo.sweep! call-equivalents (walkers x sweeps)      */
+#define KDSL_ACC_SUM_ACC 1       /* sum of the :acc observable (src/MonteCarlo.jl:548-589)          */
+#define KDSL_ACC_SUM_OL 2        /* sum of the :OL observable (src/MonteCarlo.jl:632)               */
+#define KDSL_ACC_SUM_OL2 3       /* sum of OL^2                                                      */
+#define KDSL_ACC_N_OL 4          /* number of :OL samples                                            */
+#define KDSL_ACC_N_REACH 5       /* sweeps that reached the refresh block (src/MonteCarlo.jl:594)   */
+#define KDSL_ACC_N_REFRESH 6     /* walker re-evaluations of W executed                              */
+#define KDSL_ACC_N_SINGULAR 7    /* re-evaluations that hit a singular tilde_U                       */
+#define KDSL_N_ACC 8
+
+/* indices into kdsl_timers (milliseconds of device time / launch counts per kernel class) */
+#define KDSL_T_PROPOSE 0
+#define KDSL_T_UPDATE 1
+#define KDSL_T_REFRESH_GATHER 2
+#define KDSL_T_REFRESH_INVERSE 3
+#define KDSL_T_REFRESH_GEMM 4
+#define KDSL_T_MEASURE 5
+#define KDSL_N_TIMERS 6
+
+int kdsl_version(void);
+/* thread-local message of the last failing call on this thread */
+const char *kdsl_last_error(void);
+/* number of visible CUDA devices (0 and KDSL_ERR_CUDA when there is none: there is no CPU path) */
+int kdsl_device_count(int *n);
+
+/*
+ * Create an engine on CUDA device `device`.
+ * Replaces the state built by MC(params) / MC(Ham, kappa_up, kappa_down, W_up, W_down)
+ * (src/MonteCarlo.jl:165-185, 209-234) from a Hamiltonian (src/Hamiltonian.jl:346-353):
+ *   bonds  int32 [n_bonds][2]  Ham.nn, 1-based, reference order
+ *   U_up   double [ns x n_up]  column-major Ham.U_up (real)
+ *   U_dn   double [ns x n_dn]  column-major Ham.U_down
+ * All walkers start with kappa = 0 and W = 0 like the reference (:179-182); a
+ * configuration must be supplied with kdsl_set_config before sweeping.
+ * Requires ns even (true for every DoubleKagome: ns = 3*n1*n2 with n1 even).
+ */
+int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
+                const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers);
+int kdsl_destroy(kdsl_handle h);
+
+/*
+ * Set / get the configurations of all walkers: int32 [n_walkers][ns] each.
+ * Replaces the assignments mc.kappa_up = ..., mc.kappa_down = ... of init_conf_qr!
+ * (src/MonteCarlo.jl:326-357) and read_checkpoint! (:751-755), and the reads of
+ * write_checkpoint (:715-719).  Every walker must be a Mott state (each site holds exactly one
+ * particle) whose labels are a permutation of 1..N per species, else KDSL_ERR_INVALID_ARGUMENT
+ * (the analogue of tilde_U's ArgumentError / BoundsError, src/MonteCarlo.jl:96-110).
+ * Setting a configuration invalidates W; call kdsl_refresh next (deviation from the reference,
+ * whose W stays zero after read_checkpoint!: SURVEY section 9 item 14).
+ */
+int kdsl_set_config(kdsl_handle h, const int32_t *kappa_up, const int32_t *kappa_dn);
+int kdsl_get_config(kdsl_handle h, int32_t *kappa_up, int32_t *kappa_dn);
+
+/*
+ * Per-walker Xoshiro256++ states, uint64 [n_walkers][4] (Julia's Random.Xoshiro layout s0..s3).
+ * Replaces ctx.rng (src/MonteCarlo.jl:546,552,569): the host owns seeding, the device owns the
+ * streams afterwards.
+ */
+int kdsl_set_rng(kdsl_handle h, const uint64_t *states);
+int kdsl_get_rng(kdsl_handle h, uint64_t *states);
+
+/* ctx.sweeps (src/MonteCarlo.jl:595,630): the lock-step sweep counter shared by all walkers */
+int kdsl_set_sweeps(kdsl_handle h, int64_t sweeps);
+int kdsl_get_sweeps(kdsl_handle h, int64_t *sweeps);
+
+/*
+ * reevaluateW!(mc) for every walker (src/MonteCarlo.jl:55-66): W = U * inv(tilde_U(U, kappa)).
+ * On return *n_singular (may be NULL) holds the number of walkers whose tilde_U was singular
+ * (their KDSL_FLAG_SINGULAR is set and their W is left unchanged); the status is
+ * KDSL_ERR_SINGULAR when that number is non-zero -- the SingularException of :59-60 / the
+ * "QR-based configuration is singular" error of :401-405.
+ */
+int kdsl_refresh(kdsl_handle h, int *n_singular);
+
+/*
+ * n_sweeps x { Carlo.sweep!(mc, ctx); ctx.sweeps += 1 } for every walker, random numbers drawn
+ * on the device from the walker's Xoshiro stream exactly in the reference's order
+ * (src/MonteCarlo.jl:538-607).  If thermalization >= 0 the Carlo step loop is completed:
+ * after each increment, if ctx.sweeps > thermalization, Carlo.measure! (:628-634) runs and
+ * feeds the device-side accumulators.  Pass thermalization < 0 to never measure.
+ * Asynchronous; errors of the device work surface at the next synchronising call.
+ */
+int kdsl_sweep(kdsl_handle h, int64_t n_sweeps, int64_t thermalization);
+
+/*
+ * Same as kdsl_sweep but the three random draws of each sweep are REPLAYED from host buffers
+ * laid out [n_sweeps][n_walkers]:  r (the Float64 of :546), bond_idx (1-based index into nn
+ * drawn at :552; read only if the gate :547 passes), pick (1-based index into maybe_update,
+ * :569; may be NULL = all ones).  The walkers' RNG states are not touched.  This is the parity
+ * interface, and the path a host that owns ctx.rng uses.
+ */
+int kdsl_replay(kdsl_handle h, int64_t n_sweeps, int64_t thermalization, const double *r,
+                const int32_t *bond_idx, const int32_t *pick);
+
+/*
+ * getOL(mc, kappa_up, kappa_down) for every walker, now, regardless of the cadence test
+ * (src/Hamiltonian.jl:762-778): ol double [n_walkers].  Does not touch the accumulators.
+ * KDSL_ERR_INVALID_ARGUMENT if a walker holds an empty / doubly occupied site (Sz's ArgumentError).
+ */
+int kdsl_measure(kdsl_handle h, double *ol);
+
+/*
+ * The latest :OL sample of every walker taken by the cadence inside kdsl_sweep / kdsl_replay
+ * (double [n_walkers]) and how many samples each walker has taken so far (int64 [n_walkers],
+ * may be NULL).  This is what Carlo.measure!(mc, ctx) hands to measure!(ctx, :OL, .).
+ */
+int kdsl_last_OL(kdsl_handle h, double *ol, int64_t *n_samples);
+
+/*
+ * Sums over this handle's walkers since the last reset: double [KDSL_N_ACC] (indices above).
+ * Optionally per-walker: acc_per_walker int64 [n_walkers] (accepted moves), ol_sum_per_walker
+ * double [n_walkers]; either may be NULL.  Multi-GPU jobs add these vectors across ranks.
+ */
+int kdsl_accumulators(kdsl_handle h, double *out, int64_t *acc_per_walker,
+                      double *ol_sum_per_walker);
+int kdsl_reset_accumulators(kdsl_handle h);
+
+/* Copy one walker's W matrix to the host: spin 0 = up (ns x n_up), 1 = down (ns x n_dn) */
+int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out);
+/* Overwrite one walker's W matrix (test hook for the update_W! known answers) */
+int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in);
+
+/*
+ * update_W!(W, l, K, col_cache, row_cache) (src/MonteCarlo.jl:279-292) applied to the listed
+ * walkers through the production rank-1 kernel: for m in 0..n_moves-1, walker[m]'s W_up is
+ * updated with (l_up[m], K_up[m]) and its W_down with (l_dn[m], K_dn[m]) (1-based).  Walker ids
+ * must be distinct.  kappa is not touched (test / benchmarking hook for the W-update kernel).
+ */
+int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32_t *l_up,
+                  const int32_t *K_up, const int32_t *l_dn, const int32_t *K_dn);
+
+/* Z(nn, kappa_up, kappa_down) (src/MonteCarlo.jl:460-474) of every walker:
+ * zmu = the incrementally maintained value used by the proposals, zmu_recount (may be NULL) =
+ * a full recount over the bond list; the two must agree. int32 [n_walkers] each */
+int kdsl_get_Z(kdsl_handle h, int32_t *zmu, int32_t *zmu_recount);
+
+/* per-walker KDSL_FLAG_* bits, int32 [n_walkers] */
+int kdsl_get_flags(kdsl_handle h, int32_t *flags);
+
+/*
+ * Device-time profile.  kdsl_set_profiling(h, 1) brackets every kernel launch with CUDA events on
+ * the engine's stream; kdsl_timers then returns, per kernel class, the summed device
+ * milliseconds (ms[KDSL_N_TIMERS]) and launch counts (launches[KDSL_N_TIMERS]) since the last
+ * kdsl_reset_timers, plus (any may be NULL) the number of accepted moves the W-update launches
+ * processed.  Launch counts are maintained even when profiling is off.
+ */
+int kdsl_set_profiling(kdsl_handle h, int enabled);
+int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_moves);
+int kdsl_reset_timers(kdsl_handle h);
+
+/* Tunables: name in {"refresh_every" (0 = reference cadence n_occ), "update_variant",
+ * "update_ctas_per_sm", "inverse_variant", "gemm_variant"}.  KDSL_ERR_INVALID_ARGUMENT if unknown. */
+int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);
+
+/* Block until all device work of this handle is complete; returns the first deferred error */
+int kdsl_synchronize(kdsl_handle h);
+
+/* Handle geometry: out[0..5] = ns, n_up, n_dn, n_bonds, n_walkers, n_occ (= min(n_up, n_dn),
+ * src/MonteCarlo.jl:594) */
+int kdsl_info(kdsl_handle h, int64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDSL_H */

@@ -1,0 +1,763 @@
+// kdsl_api.cu -- host side of libkdsl.so: handle, device memory, launch sequencing and the
+// extern "C" entry points declared in include/kdsl.h.  sm_100a only; there is no CPU path:
+// every entry point fails with KDSL_ERR_CUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kdsl.h"
+#include "kdsl_common.cuh"
+#include "kdsl_measure.cuh"
+#include "kdsl_propose.cuh"
+#include "kdsl_refresh.cuh"
+#include "kdsl_update.cuh"
+
+#define KDSL_VERSION_NUM 100
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(KDSL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+struct TimedSpan {
+    int cls;
+    cudaEvent_t a, b;
+};
+
+struct kdsl_handle_s {
+    int device = 0;
+    int num_sms = 148;
+    DevState S{};
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    // refresh workspace (tilde_U / inverse), sized for all walkers
+    double *A_up = nullptr, *A_dn = nullptr;
+    int *status = nullptr;
+    int *d_tmp_i = nullptr;       // [nw] scratch
+    double *d_tmp_d = nullptr;    // [nw] scratch
+    double *d_acc8 = nullptr;     // [8]
+    // replay staging (device)
+    double *rp_r = nullptr;
+    int *rp_bond = nullptr, *rp_pick = nullptr;
+    size_t rp_cap = 0;            // capacity in sweeps*walkers entries
+    // move staging for kdsl_update_W
+    int64_t sweeps = 0;
+    int parity = 0;
+    bool have_config = false, W_valid = false;
+    int64_t walker_sweeps = 0;
+    // options
+    int64_t refresh_every = 0;
+    int update_variant = 0, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
+    int update_ch = 8;
+    // profiling
+    bool profiling = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double t_ms[KDSL_N_TIMERS] = {0};
+    int64_t t_launch[KDSL_N_TIMERS] = {0};
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(kdsl_handle h, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess)
+        return fail(KDSL_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(KDSL_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return KDSL_OK;
+}
+
+int use_device(kdsl_handle h) {
+    if (!h) return fail(KDSL_ERR_INVALID_ARGUMENT, "null handle");
+    CK(cudaSetDevice(h->device));
+    return KDSL_OK;
+}
+
+cudaEvent_t get_event(kdsl_handle h) {
+    if (!h->ev_pool.empty()) {
+        cudaEvent_t e = h->ev_pool.back();
+        h->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// fold finished spans into the per-class timers (synchronises the stream)
+int flush_spans(kdsl_handle h) {
+    if (h->spans.empty()) return KDSL_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto &s : h->spans) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.a, s.b));
+        h->t_ms[s.cls] += ms;
+        h->ev_pool.push_back(s.a);
+        h->ev_pool.push_back(s.b);
+    }
+    h->spans.clear();
+    return KDSL_OK;
+}
+
+struct Span {
+    kdsl_handle h;
+    int cls;
+    cudaEvent_t a = nullptr;
+    Span(kdsl_handle h_, int cls_) : h(h_), cls(cls_) {
+        h->t_launch[cls] += 1;
+        if (h->profiling) {
+            a = get_event(h);
+            cudaEventRecord(a, h->stream);
+        }
+    }
+    ~Span() {
+        if (h->profiling) {
+            cudaEvent_t b = get_event(h);
+            cudaEventRecord(b, h->stream);
+            h->spans.push_back({cls, a, b});
+        }
+    }
+};
+
+int grid_for_warps(int nw) { return (nw * 32 + 255) / 256; }
+
+int launch_update(kdsl_handle h, int parity) {
+    const DevState &S = h->S;
+    const int CH = h->update_ch;
+    const int tiles_up = (S.n_up + CH - 1) / CH, tiles_dn = (S.n_dn + CH - 1) / CH;
+    const size_t smem = (size_t)(S.ns + CH) * sizeof(double);
+    int per_sm = h->update_ctas_per_sm > 0 ? h->update_ctas_per_sm : 4;
+    Span sp(h, KDSL_T_UPDATE);
+    k_update_ldg<256, 8><<<h->num_sms * per_sm, 256, smem, h->stream>>>(S, parity, tiles_up, tiles_dn, CH);
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
+// reevaluateW! for the walkers in `list` (device list with device count cnt[2]) or all (list = null)
+int launch_refresh(kdsl_handle h, const int *list) {
+    const DevState &S = h->S;
+    const int Nmax = std::max(S.n_up, S.n_dn);
+    {
+        Span sp(h, KDSL_T_REFRESH_GATHER);
+        k_gather_tilde<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+        CK(cudaGetLastError());
+    }
+    {
+        Span sp(h, KDSL_T_REFRESH_INVERSE);
+        const size_t smem = (size_t)Nmax * (2 * sizeof(double) + sizeof(int));
+        k_inverse_gj<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_up, 0, h->status);
+        CK(cudaGetLastError());
+        k_inverse_gj<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_dn, 1, h->status);
+        CK(cudaGetLastError());
+        k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
+        CK(cudaGetLastError());
+    }
+    {
+        Span sp(h, KDSL_T_REFRESH_GEMM);
+        constexpr int BM = 64, BN = 64;
+        const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
+        k_gemm_W_simt<BM, BN, 16><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+        CK(cudaGetLastError());
+    }
+    return KDSL_OK;
+}
+
+int ensure_replay_capacity(kdsl_handle h, size_t n) {
+    if (n <= h->rp_cap) return KDSL_OK;
+    if (h->rp_r) { cudaFree(h->rp_r); cudaFree(h->rp_bond); cudaFree(h->rp_pick); }
+    h->rp_r = nullptr; h->rp_bond = nullptr; h->rp_pick = nullptr; h->rp_cap = 0;
+    CK(cudaMalloc(&h->rp_r, n * sizeof(double)));
+    CK(cudaMalloc(&h->rp_bond, n * sizeof(int)));
+    CK(cudaMalloc(&h->rp_pick, n * sizeof(int)));
+    h->rp_cap = n;
+    return KDSL_OK;
+}
+
+// the lock-step Carlo loop: n x { sweep!; ctx.sweeps += 1; [measure!] }
+int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_pick) {
+    const DevState &S = h->S;
+    const int64_t period = h->refresh_every > 0 ? h->refresh_every : S.n_occ;
+    const int pgrid = grid_for_warps(S.nw);
+    for (int64_t s = 0; s < n; s++) {
+        const bool gate = (h->sweeps % period) == 0;            // src/MonteCarlo.jl:595 (pre-increment)
+        {
+            Span sp(h, KDSL_T_PROPOSE);
+            if (replay) {
+                const size_t off = (size_t)s * S.nw;
+                k_propose<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
+                                                              h->rp_bond + off, have_pick ? h->rp_pick + off : nullptr);
+            } else {
+                k_propose<false><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, nullptr, nullptr, nullptr);
+            }
+            CK(cudaGetLastError());
+        }
+        if (!gate) {
+            int rc = launch_update(h, h->parity);
+            if (rc) return rc;
+            h->parity ^= 1;
+        } else {
+            int rc = launch_refresh(h, S.ref_list);
+            if (rc) return rc;
+            CK(cudaMemsetAsync(S.cnt + 2, 0, sizeof(int), h->stream));
+        }
+        h->sweeps += 1;                                          // Carlo: ctx.sweeps += 1
+        h->walker_sweeps += S.nw;
+        if (therm >= 0 && h->sweeps > therm && (h->sweeps % S.n_occ) == 0) {   // :630 (post-increment)
+            Span sp(h, KDSL_T_MEASURE);
+            k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
+            CK(cudaGetLastError());
+        }
+        if (h->profiling && h->spans.size() > 16384) {
+            int rc = flush_spans(h);
+            if (rc) return rc;
+        }
+    }
+    return KDSL_OK;
+}
+
+int check_ready(kdsl_handle h) {
+    if (!h->have_config) return fail(KDSL_ERR_STATE, "no configuration set: call kdsl_set_config first");
+    if (!h->W_valid) return fail(KDSL_ERR_STATE, "W is stale: call kdsl_refresh after kdsl_set_config");
+    return KDSL_OK;
+}
+
+// stage (col, alpha*row) for explicit moves: one warp per move
+__global__ void __launch_bounds__(256)
+k_stage_moves(DevState S, int parity, int n_moves, const int *__restrict__ mv) {
+    const int m = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= n_moves) return;
+    const int w = mv[m], l_up = mv[n_moves + m], K_up = mv[2 * n_moves + m] - 1, l_dn = mv[3 * n_moves + m], K_dn = mv[4 * n_moves + m] - 1;
+    const int ns = S.ns;
+    const double *Wu = S.W_up + (size_t)w * ns * S.n_up, *Wd = S.W_dn + (size_t)w * ns * S.n_dn;
+    const double au = -1.0 / Wu[(size_t)(l_up - 1) * ns + K_up], ad = -1.0 / Wd[(size_t)(l_dn - 1) * ns + K_dn];
+    for (int t = lane; t < ns; t += 32) {
+        S.col_up[(size_t)w * ns + t] = Wu[(size_t)(l_up - 1) * ns + t];
+        S.col_dn[(size_t)w * ns + t] = Wd[(size_t)(l_dn - 1) * ns + t];
+    }
+    for (int j = lane; j < S.n_up; j += 32) {
+        double v = Wu[(size_t)j * ns + K_up];
+        if (j == l_up - 1) v -= 1.0;
+        S.trow_up[(size_t)w * S.n_up + j] = au * v;
+    }
+    for (int j = lane; j < S.n_dn; j += 32) {
+        double v = Wd[(size_t)j * ns + K_dn];
+        if (j == l_dn - 1) v -= 1.0;
+        S.trow_dn[(size_t)w * S.n_dn + j] = ad * v;
+    }
+    if (lane == 0) S.acc_list[(size_t)parity * S.nw + m] = w;
+    if (m == 0 && lane == 0) S.cnt[parity] = n_moves;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kdsl_version(void) { return KDSL_VERSION_NUM; }
+
+const char *kdsl_last_error(void) { return g_err.c_str(); }
+
+int kdsl_device_count(int *n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (n) *n = (e == cudaSuccess) ? c : 0;
+    if (e != cudaSuccess) return fail(KDSL_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    if (c == 0) return fail(KDSL_ERR_CUDA, "no CUDA device visible (libkdsl has no CPU path)");
+    return KDSL_OK;
+}
+
+int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
+                const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers) {
+    if (!out) return fail(KDSL_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (ns <= 0 || (ns & 1)) return fail(KDSL_ERR_INVALID_ARGUMENT, "ns must be positive and even, got %d", ns);
+    if (n_up <= 0 || n_dn <= 0 || n_up > ns || n_dn > ns)
+        return fail(KDSL_ERR_INVALID_ARGUMENT, "need 0 < N_up, N_down <= ns (got %d, %d, ns=%d)", n_up, n_dn, ns);
+    if (n_up + n_dn != ns)
+        return fail(KDSL_ERR_INVALID_ARGUMENT, "Mott constraint: N_up + N_down must equal ns (got %d + %d != %d)", n_up, n_dn, ns);
+    if (n_bonds <= 0 || !bonds || !U_up || !U_dn) return fail(KDSL_ERR_INVALID_ARGUMENT, "bonds / U_up / U_dn missing");
+    if (n_walkers <= 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "n_walkers must be positive");
+    for (int b = 0; b < n_bonds; b++) {
+        const int i = bonds[2 * b], j = bonds[2 * b + 1];
+        if (i < 1 || j < 1 || i > ns || j > ns || i == j)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "bond %d = (%d, %d) out of range", b + 1, i, j);
+    }
+    int ndev = 0;
+    int rc = kdsl_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(KDSL_ERR_INVALID_ARGUMENT, "device %d not in [0, %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(KDSL_ERR_CUDA, "device %d is sm_%d%d; libkdsl is built for sm_100a only", device, prop.major, prop.minor);
+
+    kdsl_handle h = new kdsl_handle_s();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    DevState &S = h->S;
+    S.ns = ns; S.n_up = n_up; S.n_dn = n_dn; S.n_bonds = n_bonds; S.nw = n_walkers;
+    S.n_occ = std::min(n_up, n_dn);                               // src/MonteCarlo.jl:594
+    const size_t nw = n_walkers;
+
+#define ALLOC(ptr, n)                                        \
+    do {                                                     \
+        rc = dev_alloc(h, &(ptr), (n));                      \
+        if (rc) { kdsl_destroy(h); return rc; }              \
+    } while (0)
+#define CKD(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            kdsl_destroy(h);                                                               \
+            return fail(KDSL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));    \
+        }                                                                                  \
+    } while (0)
+
+    CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    int *bi, *bj, *adj_off, *adj_nbr;
+    double *dUu, *dUd;
+    ALLOC(bi, n_bonds); ALLOC(bj, n_bonds); ALLOC(adj_off, ns + 1); ALLOC(adj_nbr, 2 * (size_t)n_bonds);
+    ALLOC(dUu, (size_t)ns * n_up); ALLOC(dUd, (size_t)ns * n_dn);
+    {
+        std::vector<int> hbi(n_bonds), hbj(n_bonds), off(ns + 1, 0), nbr(2 * (size_t)n_bonds);
+        for (int b = 0; b < n_bonds; b++) {
+            hbi[b] = bonds[2 * b] - 1; hbj[b] = bonds[2 * b + 1] - 1;
+            off[hbi[b] + 1]++; off[hbj[b] + 1]++;
+        }
+        for (int s = 0; s < ns; s++) off[s + 1] += off[s];
+        std::vector<int> fill(off.begin(), off.end() - 1);
+        for (int b = 0; b < n_bonds; b++) {
+            nbr[fill[hbi[b]]++] = hbj[b];
+            nbr[fill[hbj[b]]++] = hbi[b];
+        }
+        CKD(cudaMemcpy(bi, hbi.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(bj, hbj.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(adj_off, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(adj_nbr, nbr.data(), 2 * (size_t)n_bonds * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(dUu, U_up, (size_t)ns * n_up * sizeof(double), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(dUd, U_dn, (size_t)ns * n_dn * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    S.bi = bi; S.bj = bj; S.adj_off = adj_off; S.adj_nbr = adj_nbr; S.U_up = dUu; S.U_dn = dUd;
+    ALLOC(S.kup, nw * ns); ALLOC(S.kdn, nw * ns);
+    ALLOC(S.rng, nw * 4); ALLOC(S.zmu, nw);
+    ALLOC(S.W_up, nw * ns * n_up); ALLOC(S.W_dn, nw * ns * n_dn);
+    ALLOC(S.col_up, nw * ns); ALLOC(S.col_dn, nw * ns);
+    ALLOC(S.trow_up, nw * n_up); ALLOC(S.trow_dn, nw * n_dn);
+    ALLOC(S.acc_list, 2 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
+    ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
+    ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 1);
+    ALLOC(h->A_up, nw * n_up * n_up); ALLOC(h->A_dn, nw * n_dn * n_dn);
+    ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
+#undef ALLOC
+    // default xoshiro states must not be all-zero: seed walker w with a fixed SplitMix64 stream
+    {
+        std::vector<unsigned long long> st(nw * 4);
+        unsigned long long x = 0x243F6A8885A308D3ull;
+        for (auto &v : st) {
+            unsigned long long z = (x += 0x9E3779B97F4A7C15ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            v = z ^ (z >> 31);
+        }
+        CKD(cudaMemcpy(S.rng, st.data(), st.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    CKD(cudaFuncSetAttribute(k_inverse_gj, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+#undef CKD
+    *out = h;
+    return KDSL_OK;
+}
+
+int kdsl_destroy(kdsl_handle h) {
+    if (!h) return KDSL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->rp_r) { cudaFree(h->rp_r); cudaFree(h->rp_bond); cudaFree(h->rp_pick); }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return KDSL_OK;
+}
+
+int kdsl_info(kdsl_handle h, int64_t *out) {
+    if (!h || !out) return fail(KDSL_ERR_INVALID_ARGUMENT, "null argument");
+    out[0] = h->S.ns; out[1] = h->S.n_up; out[2] = h->S.n_dn; out[3] = h->S.n_bonds; out[4] = h->S.nw; out[5] = h->S.n_occ;
+    return KDSL_OK;
+}
+
+int kdsl_set_config(kdsl_handle h, const int32_t *kup, const int32_t *kdn) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!kup || !kdn) return fail(KDSL_ERR_INVALID_ARGUMENT, "kappa_up / kappa_dn is null");
+    const DevState &S = h->S;
+    std::vector<char> seen(std::max(S.n_up, S.n_dn) + 1);
+    for (int w = 0; w < S.nw; w++) {
+        const int32_t *ku = kup + (size_t)w * S.ns, *kd = kdn + (size_t)w * S.ns;
+        for (int spin = 0; spin < 2; spin++) {
+            const int32_t *k = spin ? kd : ku;
+            const int N = spin ? S.n_dn : S.n_up;
+            std::fill(seen.begin(), seen.end(), 0);
+            int cnt = 0;
+            for (int R = 0; R < S.ns; R++) {
+                const int l = k[R];
+                if (l == 0) continue;
+                if (l < 1 || l > N)
+                    return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: kappa_%s[%d] = %d is not a label in 1..%d (BoundsError in tilde_U)",
+                                w, spin ? "down" : "up", R + 1, l, N);
+                if (seen[l])
+                    return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: label %d appears twice in kappa_%s", w, l, spin ? "down" : "up");
+                seen[l] = 1;
+                cnt++;
+            }
+            if (cnt != N)
+                return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: kappa_%s holds %d particles, expected %d (kappa is not valid)",
+                            w, spin ? "down" : "up", cnt, N);
+        }
+        for (int R = 0; R < S.ns; R++)
+            if ((ku[R] != 0) == (kd[R] != 0))
+                return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: site %d is %s (not a Mott state)", w, R + 1,
+                            ku[R] != 0 ? "doubly occupied" : "unoccupied");
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(S.kup, kup, (size_t)S.nw * S.ns * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S.kdn, kdn, (size_t)S.nw * S.ns * sizeof(int), cudaMemcpyHostToDevice));
+    k_count_Z<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, nullptr, 1);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(S.cnt, 0, 8 * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(S.flags, 0, (size_t)S.nw * sizeof(int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->parity = 0;
+    h->have_config = true;
+    h->W_valid = false;
+    return KDSL_OK;
+}
+
+int kdsl_get_config(kdsl_handle h, int32_t *kup, int32_t *kdn) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!kup || !kdn) return fail(KDSL_ERR_INVALID_ARGUMENT, "null output");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(kup, h->S.kup, (size_t)h->S.nw * h->S.ns * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(kdn, h->S.kdn, (size_t)h->S.nw * h->S.ns * sizeof(int), cudaMemcpyDeviceToHost));
+    return KDSL_OK;
+}
+
+int kdsl_set_rng(kdsl_handle h, const uint64_t *states) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!states) return fail(KDSL_ERR_INVALID_ARGUMENT, "states is null");
+    for (int w = 0; w < h->S.nw; w++)
+        if (!(states[4 * w] | states[4 * w + 1] | states[4 * w + 2] | states[4 * w + 3]))
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: all-zero Xoshiro state", w);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->S.rng, states, (size_t)h->S.nw * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    return KDSL_OK;
+}
+
+int kdsl_get_rng(kdsl_handle h, uint64_t *states) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!states) return fail(KDSL_ERR_INVALID_ARGUMENT, "states is null");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(states, h->S.rng, (size_t)h->S.nw * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return KDSL_OK;
+}
+
+int kdsl_set_sweeps(kdsl_handle h, int64_t sweeps) {
+    if (!h) return fail(KDSL_ERR_INVALID_ARGUMENT, "null handle");
+    if (sweeps < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "sweeps must be >= 0");
+    h->sweeps = sweeps;
+    return KDSL_OK;
+}
+
+int kdsl_get_sweeps(kdsl_handle h, int64_t *sweeps) {
+    if (!h || !sweeps) return fail(KDSL_ERR_INVALID_ARGUMENT, "null argument");
+    *sweeps = h->sweeps;
+    return KDSL_OK;
+}
+
+int kdsl_refresh(kdsl_handle h, int *n_singular) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!h->have_config) return fail(KDSL_ERR_STATE, "no configuration set: call kdsl_set_config first");
+    CK(cudaMemsetAsync(h->S.cnt + 3, 0, sizeof(int), h->stream));
+    rc = launch_refresh(h, nullptr);
+    if (rc) return rc;
+    int ns_ = 0;
+    CK(cudaMemcpyAsync(&ns_, h->S.cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (n_singular) *n_singular = ns_;
+    h->W_valid = true;
+    if (ns_ > 0) return fail(KDSL_ERR_SINGULAR, "SingularException: tilde_U is singular for %d walker(s)", ns_);
+    return KDSL_OK;
+}
+
+int kdsl_sweep(kdsl_handle h, int64_t n_sweeps, int64_t thermalization) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = check_ready(h))) return rc;
+    if (n_sweeps < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "n_sweeps must be >= 0");
+    return run_sweeps(h, n_sweeps, thermalization, false, false);
+}
+
+int kdsl_replay(kdsl_handle h, int64_t n_sweeps, int64_t thermalization, const double *r,
+                const int32_t *bond_idx, const int32_t *pick) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = check_ready(h))) return rc;
+    if (n_sweeps < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "n_sweeps must be >= 0");
+    if (n_sweeps == 0) return KDSL_OK;
+    if (!r || !bond_idx) return fail(KDSL_ERR_INVALID_ARGUMENT, "r / bond_idx is null");
+    const size_t n = (size_t)n_sweeps * h->S.nw;
+    if ((rc = ensure_replay_capacity(h, n))) return rc;
+    CK(cudaMemcpyAsync(h->rp_r, r, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->rp_bond, bond_idx, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (pick) CK(cudaMemcpyAsync(h->rp_pick, pick, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return run_sweeps(h, n_sweeps, thermalization, true, pick != nullptr);
+}
+
+int kdsl_measure(kdsl_handle h, double *ol) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = check_ready(h))) return rc;
+    if (!ol) return fail(KDSL_ERR_INVALID_ARGUMENT, "ol is null");
+    const DevState &S = h->S;
+    {
+        Span sp(h, KDSL_T_MEASURE);
+        k_measure<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(ol, h->d_tmp_d, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int> fl(S.nw);
+    CK(cudaMemcpyAsync(fl.data(), S.flags, (size_t)S.nw * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int w = 0; w < S.nw; w++)
+        if (fl[w] & KDSL_FLAG_BAD_SITE)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: a site is unoccupied or doubly occupied (ArgumentError in Sz)", w);
+    return KDSL_OK;
+}
+
+int kdsl_last_OL(kdsl_handle h, double *ol, int64_t *n_samples) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!ol) return fail(KDSL_ERR_INVALID_ARGUMENT, "ol is null");
+    const DevState &S = h->S;
+    CK(cudaMemcpyAsync(ol, S.ol_last, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (n_samples)
+        CK(cudaMemcpyAsync(n_samples, S.ol_n, (size_t)S.nw * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KDSL_OK;
+}
+
+int kdsl_accumulators(kdsl_handle h, double *out, int64_t *acc_per_walker, double *ol_sum_per_walker) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!out) return fail(KDSL_ERR_INVALID_ARGUMENT, "out is null");
+    const DevState &S = h->S;
+    k_reduce_acc<<<1, 1024, 0, h->stream>>>(S, h->d_acc8);
+    CK(cudaGetLastError());
+    double tmp[8];
+    int cnt3 = 0;
+    CK(cudaMemcpyAsync(tmp, h->d_acc8, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&cnt3, S.cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (acc_per_walker)
+        CK(cudaMemcpyAsync(acc_per_walker, S.n_acc, (size_t)S.nw * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (ol_sum_per_walker)
+        CK(cudaMemcpyAsync(ol_sum_per_walker, S.ol_sum, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    out[KDSL_ACC_WALKER_SWEEPS] = (double)h->walker_sweeps;
+    out[KDSL_ACC_SUM_ACC] = tmp[1];
+    out[KDSL_ACC_SUM_OL] = tmp[2];
+    out[KDSL_ACC_SUM_OL2] = tmp[3];
+    out[KDSL_ACC_N_OL] = tmp[4];
+    out[KDSL_ACC_N_REACH] = tmp[5];
+    out[KDSL_ACC_N_REFRESH] = tmp[6];
+    out[KDSL_ACC_N_SINGULAR] = (double)cnt3;
+    return KDSL_OK;
+}
+
+int kdsl_reset_accumulators(kdsl_handle h) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    const DevState &S = h->S;
+    const size_t nw = S.nw;
+    CK(cudaMemsetAsync(S.n_acc, 0, nw * 8, h->stream));
+    CK(cudaMemsetAsync(S.n_reach, 0, nw * 8, h->stream));
+    CK(cudaMemsetAsync(S.n_refresh, 0, nw * 8, h->stream));
+    CK(cudaMemsetAsync(S.ol_sum, 0, nw * 8, h->stream));
+    CK(cudaMemsetAsync(S.ol_sq, 0, nw * 8, h->stream));
+    CK(cudaMemsetAsync(S.ol_n, 0, nw * 8, h->stream));
+    CK(cudaMemsetAsync(S.cnt + 3, 0, sizeof(int), h->stream));
+    h->walker_sweeps = 0;
+    return KDSL_OK;
+}
+
+int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    const DevState &S = h->S;
+    if (!out || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / out");
+    const int N = spin ? S.n_dn : S.n_up;
+    const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double), cudaMemcpyDeviceToHost));
+    return KDSL_OK;
+}
+
+int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    const DevState &S = h->S;
+    if (!in || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / in");
+    const int N = spin ? S.n_dn : S.n_up;
+    double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double), cudaMemcpyHostToDevice));
+    return KDSL_OK;
+}
+
+int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32_t *l_up,
+                  const int32_t *K_up, const int32_t *l_dn, const int32_t *K_dn) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    const DevState &S = h->S;
+    if (n_moves < 0 || n_moves > S.nw) return fail(KDSL_ERR_INVALID_ARGUMENT, "n_moves must be in [0, n_walkers]");
+    if (n_moves == 0) return KDSL_OK;
+    if (!walker || !l_up || !K_up || !l_dn || !K_dn) return fail(KDSL_ERR_INVALID_ARGUMENT, "null move array");
+    std::vector<char> used(S.nw, 0);
+    std::vector<int> mv(5 * (size_t)n_moves);
+    for (int m = 0; m < n_moves; m++) {
+        if (walker[m] < 0 || walker[m] >= S.nw || used[walker[m]]) return fail(KDSL_ERR_INVALID_ARGUMENT, "move %d: walker id invalid or repeated", m);
+        used[walker[m]] = 1;
+        if (l_up[m] < 1 || l_up[m] > S.n_up || l_dn[m] < 1 || l_dn[m] > S.n_dn || K_up[m] < 1 || K_up[m] > S.ns || K_dn[m] < 1 || K_dn[m] > S.ns)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "move %d: label or site out of range (BoundsError)", m);
+        mv[m] = walker[m]; mv[n_moves + m] = l_up[m]; mv[2 * (size_t)n_moves + m] = K_up[m];
+        mv[3 * (size_t)n_moves + m] = l_dn[m]; mv[4 * (size_t)n_moves + m] = K_dn[m];
+    }
+    int *d_mv = nullptr;
+    CK(cudaMalloc(&d_mv, mv.size() * sizeof(int)));
+    CK(cudaMemcpyAsync(d_mv, mv.data(), mv.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_stage_moves<<<grid_for_warps(n_moves), 256, 0, h->stream>>>(S, h->parity, n_moves, d_mv);
+    CK(cudaGetLastError());
+    rc = launch_update(h, h->parity);
+    h->parity ^= 1;
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_mv);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
+int kdsl_get_Z(kdsl_handle h, int32_t *zmu, int32_t *zmu_recount) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    const DevState &S = h->S;
+    if (!zmu) return fail(KDSL_ERR_INVALID_ARGUMENT, "zmu is null");
+    if (zmu_recount) {
+        k_count_Z<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_i, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(zmu_recount, h->d_tmp_i, (size_t)S.nw * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaMemcpyAsync(zmu, S.zmu, (size_t)S.nw * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KDSL_OK;
+}
+
+int kdsl_get_flags(kdsl_handle h, int32_t *flags) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!flags) return fail(KDSL_ERR_INVALID_ARGUMENT, "flags is null");
+    CK(cudaMemcpyAsync(flags, h->S.flags, (size_t)h->S.nw * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KDSL_OK;
+}
+
+int kdsl_set_profiling(kdsl_handle h, int enabled) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!enabled && h->profiling) {
+        rc = flush_spans(h);
+        if (rc) return rc;
+    }
+    h->profiling = enabled != 0;
+    return KDSL_OK;
+}
+
+int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_moves) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = flush_spans(h))) return rc;
+    if (ms) memcpy(ms, h->t_ms, sizeof h->t_ms);
+    if (launches) memcpy(launches, h->t_launch, sizeof h->t_launch);
+    if (update_moves) {
+        unsigned long long v = 0;
+        CK(cudaMemcpy(&v, h->S.upd_moves, sizeof v, cudaMemcpyDeviceToHost));
+        *update_moves = (int64_t)v;
+    }
+    return KDSL_OK;
+}
+
+int kdsl_reset_timers(kdsl_handle h) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = flush_spans(h))) return rc;
+    memset(h->t_ms, 0, sizeof h->t_ms);
+    memset(h->t_launch, 0, sizeof h->t_launch);
+    CK(cudaMemset(h->S.upd_moves, 0, sizeof(unsigned long long)));
+    return KDSL_OK;
+}
+
+int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
+    if (!h || !name) return fail(KDSL_ERR_INVALID_ARGUMENT, "null argument");
+    const std::string n(name);
+    if (n == "refresh_every") {
+        if (value < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "refresh_every must be >= 0");
+        h->refresh_every = value;
+    } else if (n == "update_variant") h->update_variant = (int)value;
+    else if (n == "update_ctas_per_sm") h->update_ctas_per_sm = (int)value;
+    else if (n == "update_cols_per_item") {
+        if (value < 1 || value > 4096) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_cols_per_item out of range");
+        h->update_ch = (int)value;
+    } else if (n == "inverse_variant") h->inverse_variant = (int)value;
+    else if (n == "gemm_variant") h->gemm_variant = (int)value;
+    else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
+    return KDSL_OK;
+}
+
+int kdsl_synchronize(kdsl_handle h) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): configurations / Z / counters bit-exact under a replayed proposal
+sequence; W, determinant ratios and O_L within 1e-10 relative of the FP64 reference path.
+"""
+import numpy as np
+import pytest
+
+import _util as U
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def kd():
+    import kagomedsl.jl_b200 as kd_
+    if kd_._lib.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    return kd_
+
+
+@pytest.mark.parametrize("n1,n2,PBC,anti,flux", [
+    (2, 2, (False, False), (False, False), "pi"),       # the reference's own test lattice (test-MonteCarlo.jl:480)
+    (4, 3, (True, True), (True, False), "pi"),          # SURVEY config 1
+    (6, 6, (True, True), (True, False), "pi"),          # config 2
+    (6, 6, (True, True), (True, False), "zero"),
+])
+def test_refresh_matches_oracle(kd, n1, n2, PBC, anti, flux):
+    lat, ham = U.problem(n1, n2, PBC, anti, flux)
+    ns, nw = kd.ns(lat), 6
+    rng = np.random.default_rng(11)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    z, zr = eng.Z()
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+        assert z[w] == zr[w] == U.O.Z(ham.nn, ku[w], kdn[w])
+    # rows of W at occupied sites are unit vectors (SURVEY 8(a) invariant)
+    W0 = eng.get_W(0, 0)
+    occ = np.nonzero(ku[0])[0]
+    assert np.allclose(W0[occ, :][np.arange(len(occ)), ku[0][occ] - 1], 1.0, atol=1e-9)
+    eng.close()
+
+
+def test_update_W_matches_oracle_and_formula(kd):
+    lat, ham = U.problem(4, 3)
+    ns, nw = kd.ns(lat), 5
+    rng = np.random.default_rng(5)
+    eng = kd.Engine(ham, nw)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    Wu0 = [rng.standard_normal((ns, ham.N_up)) for _ in range(nw)]
+    Wd0 = [rng.standard_normal((ns, ham.N_down)) for _ in range(nw)]
+    for w in range(nw):
+        eng.set_W(w, 0, Wu0[w])
+        eng.set_W(w, 1, Wd0[w])
+    walkers = np.array([3, 0, 4], dtype=np.int32)
+    l_up = np.array([1, ham.N_up, 7]); K_up = np.array([ns, 1, 20])
+    l_dn = np.array([2, 5, ham.N_down]); K_dn = np.array([1, ns, 9])
+    eng.update_W(walkers, l_up, K_up, l_dn, K_dn)
+    for m, w in enumerate(walkers):
+        for spin, (W0, l, K) in enumerate(((Wu0[w], l_up[m], K_up[m]), (Wd0[w], l_dn[m], K_dn[m]))):
+            ref = np.asfortranarray(W0.copy())
+            U.O.update_W(ref, int(l), int(K), "f64")
+            got = eng.get_W(int(w), spin)
+            assert np.array_equal(got, ref) or U.relerr(got, ref) < 1e-14      # same fma order as the oracle
+            # element formula of the reference test (test-MonteCarlo.jl:235-252)
+            I, j = 3, 4
+            d = 1.0 if j == l else 0.0
+            assert np.isclose(got[I - 1, j - 1], W0[I - 1, j - 1] - W0[I - 1, l - 1] / W0[K - 1, l - 1] * (W0[K - 1, j - 1] - d), rtol=1e-12)
+    for w in (1, 2):                                                           # untouched walkers
+        assert np.array_equal(eng.get_W(w, 0), Wu0[w])
+    eng.close()
+
+
+@pytest.mark.parametrize("n1,n2,nw,n_sweeps", [(2, 2, 8, 600), (4, 3, 8, 1500), (6, 6, 6, 2500)])
+def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps):
+    """replayed (r, bond) sequence: kappa, Z, acceptance counters bit-exact; W within 1e-10"""
+    PBC, anti = ((False, False), (False, False)) if n1 == 2 else ((True, True), (True, False))
+    lat, ham = U.problem(n1, n2, PBC, anti)
+    ns = kd.ns(lat)
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ham.N_up)
+    ku = np.tile(ku0, (nw, 1)); kdn = np.tile(kd0, (nw, 1))
+    rng = np.random.default_rng(2024 + n1)
+    nb = len(ham.nn)
+    r = rng.random((n_sweeps, nw))
+    bond = rng.integers(1, nb + 1, size=(n_sweeps, nw)).astype(np.int32)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    orc = U.oracle_walkers(ham, ku, kdn)
+    done = 0
+    for chunk in (1, 7, n_sweeps // 3, n_sweeps - 8 - n_sweeps // 3):
+        eng.replay(r[done:done + chunk], bond[done:done + chunk])
+        acc_o = 0
+        for w, mc in enumerate(orc):
+            for s in range(done, done + chunk):
+                mc.sweep(replay=(r[s, w], int(bond[s, w]), 1))
+                mc.sweeps = mc.sweeps + 1
+        done += chunk
+        gku, gkd = eng.get_config()
+        z, zr = eng.Z()
+        for w, mc in enumerate(orc):
+            oku, okd = mc.kappa()
+            assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd), f"kappa differs, walker {w} after {done} sweeps"
+            assert z[w] == zr[w] == U.O.Z(ham.nn, oku, okd)
+            Wu, Wd = mc.W()
+            assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+            assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+    acc, acc_w, _ = eng.accumulators(per_walker=True)
+    for w, mc in enumerate(orc):
+        c = mc.counters()
+        assert acc_w[w] == c[0]
+    assert acc[kd._lib.ACC_N_REACH] == sum(mc.counters()[1] for mc in orc)
+    assert acc[kd._lib.ACC_N_REFRESH] == sum(mc.counters()[2] for mc in orc)
+    assert eng.sweeps == n_sweeps
+    eng.close()
+
+
+def test_device_rng_matches_xoshiro_stream(kd):
+    """device-drawn random numbers follow Julia's Xoshiro256++ conventions: same
+    trajectory and same final generator state as the oracle fed with the same initial states"""
+    lat, ham = U.problem(4, 3)
+    ns, nw, n = kd.ns(lat), 8, 3000
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ham.N_up)
+    states = kd.walker_states(1234, nw)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku0, kd0)
+    eng.set_rng(states)
+    eng.refresh()
+    eng.sweep(n, thermalization=100)
+    gku, gkd = eng.get_config()
+    gst = eng.get_rng()
+    acc, acc_w, ol_w = eng.accumulators(per_walker=True)
+    tot = np.zeros(4)
+    for w in range(nw):
+        mc = U.oracle_walkers(ham, ku0[None], kd0[None])[0]
+        g = U.O.Xoshiro(states[w])
+        st, _ = mc.run(g, n, 100)
+        oku, okd = mc.kappa()
+        assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd)
+        assert np.array_equal(gst[w], g.s)
+        assert acc_w[w] == st[0]
+        assert abs(ol_w[w] - st[1]) <= 1e-9 * max(1.0, abs(st[1]))
+        tot += st
+    assert acc[kd._lib.ACC_N_OL] == tot[3]
+    assert abs(acc[kd._lib.ACC_SUM_OL] - tot[1]) <= 1e-9 * abs(tot[1])
+    assert acc[kd._lib.ACC_WALKER_SWEEPS] == n * nw
+    eng.close()
+
+
+def test_measure_matches_oracle_getOL(kd):
+    lat, ham = U.problem(6, 6)
+    ns, nw = kd.ns(lat), 6
+    rng = np.random.default_rng(3)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    ol = eng.measure()
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
+        ref = mc.getOL()
+        assert abs(ol[w] - ref) <= TOL * max(1.0, abs(ref))
+    eng.close()
+
+
+def test_error_paths(kd):
+    lat, ham = U.problem(2, 2, (False, False), (False, False))
+    eng = kd.Engine(ham, 2)
+    with pytest.raises(kd.KdslError):
+        eng.sweep(1)                                    # no configuration yet
+    bad = np.zeros((2, 12), dtype=np.int64)
+    with pytest.raises(kd.KdslError):
+        eng.set_config(bad, bad)                        # not a Mott state
+    ku0, kd0 = kd.init_conf_qr(ham, 12, 6)
+    eng.set_config(ku0, kd0)
+    with pytest.raises(kd.KdslError):
+        eng.sweep(1)                                    # W stale
+    eng.refresh()
+    eng.sweep(10)
+    eng.close()
+    # rank-deficient orbitals -> SingularException (reference: test-MonteCarlo.jl:429-477)
+    Ud = np.zeros((12, 6)); Ud[:6] = np.eye(6)
+    ham2 = kd.Hamiltonian(6, 6, Ud, Ud, ham.H_mat, ham.nn)
+    eng2 = kd.Engine(ham2, 1)
+    ku = np.zeros(12, dtype=np.int64); ku[6:] = np.arange(1, 7)
+    kdn = np.zeros(12, dtype=np.int64); kdn[:6] = np.arange(1, 7)
+    eng2.set_config(ku, kdn)
+    with pytest.raises(kd.SingularException):
+        eng2.refresh()
+    assert eng2.flags()[0] & 1
+    eng2.close()
+
+
+def test_exact_energy_12_sites(kd):
+    """<E>/site of the chain's stationary law |psi|^2 / Z_mu on the reference's 2x2 OBC test lattice:
+    exact enumeration gives -0.3714938624 (tests/golden/exact_energies.json)"""
+    lat, ham = U.problem(2, 2, (False, False), (False, False))
+    nw, therm, n = 2048, 2000, 12000
+    mc = kd.MC({"n1": 2, "n2": 2, "PBC": (False, False), "N_up": 6, "N_down": 6, "n_walkers": nw})
+    ctx = kd.MCContext({"thermalization": therm, "seed": 99, "binsize": 1})
+    kd.init_(mc, ctx, {"n1": 2, "n2": 2, "N_up": 6})
+    kd.run_(mc, ctx, therm + n)
+    out, acc_w, ol_w = mc.engine.accumulators(per_walker=True)
+    _, n_w = mc.engine.last_OL()
+    per_walker = ol_w / n_w / 12.0
+    mean = per_walker.mean()
+    err = per_walker.std(ddof=1) / np.sqrt(nw)
+    assert abs(mean - (-0.3714938624)) < 5 * err + 1e-5, (mean, err)
+    assert err < 5e-4
