@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- walker-sweeps/sec of the VMC sampling path at the 432-site pi-flux DSL
+(BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one bin of the hot path for every walker: n_occ = 216 lock-step Carlo sweeps (each ONE
+proposal per walker, src/MonteCarlo.jl:538-607, including the accepted-move W updates and the periodic
+re-evaluation of W) followed by one O_L measurement (src/MonteCarlo.jl:628-634).
+Workload = BASELINE.json configs[2] restricted to what one GPU holds: 12x12 DoubleKagome (432 sites),
+pi-flux, PBC, antiPBC=(true,false), N_up = N_down = 216, 4096 walkers per GPU (weak scaling:
+32768 walkers on 8 GPUs).  Each walker's W is 1.49 MB, 6.1 GB per GPU >> the 126 MB L2, so every
+timed iteration streams its inputs from HBM (no L2 flush needed).
+
+The `--impl reference` arm times the CPU restatement of the reference's algorithm (oracle/, ComplexF64 W
+like the reference) on all host cores: the reference itself is Julia and cannot run in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "walker_sweeps_per_sec_432site_piflux_dsl"
+UNIT = "walker-sweeps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lattice", type=int, default=12, help="n1 = n2 (12 -> 432 sites)")
+    ap.add_argument("--walkers-per-gpu", type=int, default=4096)
+    ap.add_argument("--thermalization", type=int, default=-1, help="untimed sweeps before warm-up (default 10*ns)")
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n, nw):
+    return f"{n}x{n} DoubleKagome ({3*n*n} sites) pi-flux DSL, PBC, antiPBC=(true,false), half filling, {nw} walkers/GPU"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference algorithm, ComplexF64) on all host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_walker_sweeps(ham, kup, kdn, seed, sweeps_per_walker, n_threads, dtype="c128"):
+    """every thread advances its own reference walker by `sweeps_per_walker` Carlo steps
+    (thermalization 0, i.e. O_L measured every n_occ sweeps); returns (walker_sweeps, seconds, E/site)"""
+    from oracle import oracle as O
+    bonds = np.asarray(ham.nn, dtype=np.int32)
+    mcs = []
+    for t in range(n_threads):
+        mc = O.MC(bonds, ham.U_up, ham.U_down, dtype)
+        mc.set_kappa(kup, kdn)
+        mc.reevaluateW()
+        mcs.append((mc, O.Xoshiro.from_seed(seed + 7919 * t), np.zeros(4)))
+    def work(t):
+        mc, g, st = mcs[t]
+        mc.run(g, sweeps_per_walker, 0, stats=st)
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    t0 = time.perf_counter()
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    dt = time.perf_counter() - t0
+    tot = sum(m[2] for m in mcs)
+    e = tot[1] / tot[3] / len(kup) if tot[3] else float("nan")
+    return n_threads * sweeps_per_walker, dt, e, mcs
+
+
+def setup_problem(n):
+    import kagomedsl.jl_b200 as kd
+    lat = kd.DoubleKagome(1.0, n, n, (True, True), (True, False))
+    ns = kd.ns(lat)
+    ham = kd.Hamiltonian(ns // 2, ns // 2, lat)
+    kup, kdn = kd.init_conf_qr(ham, ns, ns // 2)
+    return kd, lat, ham, ns, kup, kdn
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kd, lat, ham, ns, kup, kdn = setup_problem(args.lattice)
+    n_occ = ns // 2
+    cores = os.cpu_count() or 1
+    from oracle import oracle as O
+    O.build()
+    bonds = np.asarray(ham.nn, dtype=np.int32)
+    bins_per_step = 8          # one reference step: every core advances its walker by 8 bins (8*n_occ sweeps)
+    sweeps = bins_per_step * n_occ
+    mcs = []
+    for t in range(cores):
+        mc = O.MC(bonds, ham.U_up, ham.U_down, "c128")
+        mc.set_kappa(kup, kdn)
+        mc.reevaluateW()
+        mcs.append((mc, O.Xoshiro.from_seed(args.seed + 7919 * t), np.zeros(4)))
+    def one_step():
+        def work(t):
+            mc, g, st = mcs[t]
+            mc.run(g, sweeps, 0, stats=st)
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    value = cores * sweeps * args.steps / dt
+    tot = sum(m[2] for m in mcs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": workload_name(args.lattice, args.walkers_per_gpu),
+                   "note": "CPU restatement (oracle/) of the Julia reference, ComplexF64 W, one walker per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} walkers x {sweeps} sweeps per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "E_per_site": tot[1] / tot[3] / ns if tot[3] else None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    kd, lat, ham, ns, kup, kdn = setup_problem(args.lattice)
+    from kagomedsl.jl_b200 import _lib
+    n_occ = ns // 2
+    nw = args.walkers_per_gpu
+    K, W = args.steps, args.warmup
+    mc = kd.MC({"n1": args.lattice, "n2": args.lattice, "PBC": (True, True), "antiPBC": (True, False), "N_up": ns // 2,
+                "N_down": ns // 2, "n_walkers": nw, "device": local})
+    # public-API initialisation; walker streams are disjoint across ranks
+    mc.load_configuration(kup, kdn, kd.walker_states(args.seed, nw, first_walker=rank * nw))
+    eng = mc.engine
+    ctx = kd.MCContext({"thermalization": 0, "seed": args.seed})
+    therm = args.thermalization if args.thermalization >= 0 else 10 * ns
+    therm = (therm // n_occ) * n_occ                    # keep the bin phase aligned
+    eng.sweeps = 0
+    eng.sweep(therm, -1)
+    ctx.sweeps = therm
+    for _ in range(W):                                  # warm-up steps through the public API
+        kd.run_(mc, ctx, n_occ)
+    eng.synchronize()
+    eng.reset_accumulators()
+    eng.reset_timers()
+    eng.set_profiling(True)                             # CUDA events around every launch on the engine's stream
+
+    # ---- timed region: K steps, device-timed on the launching stream, max over ranks ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    eng.event_record(0)
+    for _ in range(K):
+        kd.run_(mc, ctx, n_occ)
+    eng.event_record(1)
+    eng.synchronize()
+    barrier()
+    ms = allmax(eng.event_elapsed_ms(0, 1))
+    clocks = sampler.stop() if sampler else None
+    tm = eng.timers()
+    eng.set_profiling(False)
+    res = kd.accumulators(mc)                            # NCCL all-reduce of the observable accumulators
+    total_walkers = nw * world
+    value = total_walkers * n_occ * K / (ms * 1e-3)
+    launches = sum(v["launches"] for v in tm.values())
+    B_acc = 16 * ns * ns                                 # algorithmic bytes per accepted move
+    upd = tm["update"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = upd["moves"] * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_update (Sherman-Morrison rank-1 W update)", "achieved": achieved, "peak": peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "moves_per_launch": upd["moves"] / max(upd["launches"], 1), "algorithmic_bytes_per_move": B_acc,
+                "avg_launch_us": 1e3 * upd["ms"] / max(upd["launches"], 1),
+                "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("k_update_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: same work through the public API with HOST buffers (replayed proposal stream) ----
+    e2e = None
+    if not args.no_e2e:
+        Ke = max(1, min(K, 5))
+        rng = np.random.default_rng(args.seed + 17 * rank)
+        r_host = torch.empty((Ke, n_occ, nw), dtype=torch.float64, pin_memory=True)
+        b_host = torch.empty((Ke, n_occ, nw), dtype=torch.int32, pin_memory=True)
+        r_host.copy_(torch.from_numpy(rng.random((Ke, n_occ, nw))))
+        b_host.copy_(torch.from_numpy(rng.integers(1, len(ham.nn) + 1, size=(Ke, n_occ, nw)).astype(np.int32)))
+        r_np, b_np = r_host.numpy(), b_host.numpy()
+        eng.sweeps = ctx.sweeps
+        eng.replay(r_np[0], b_np[0], thermalization=0)      # warm the path once (untimed)
+        eng.last_OL()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            eng.replay(r_np[k], b_np[k], thermalization=0)  # H2D of this step's proposal stream + 216 sweeps + measure
+            ol, n_ol = eng.last_OL()                        # D2H of the step's result
+            acc_vec = eng.accumulators()
+        barrier()
+        dt = allmax(time.perf_counter() - t0)
+        e2e = {"value": total_walkers * n_occ * Ke / dt, "unit": UNIT, "steps": Ke,
+               "h2d_bytes_per_step": int(n_occ * nw * (8 + 4)), "d2h_bytes_per_step": int(nw * 16 + 64),
+               "mode": "kdsl_replay: host supplies (r, bond) for every proposal from pinned memory; O_L and counters copied back"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        probe_ws, probe_dt, _, _ = cpu_walker_sweeps(ham, kup, kdn, args.seed, 2 * n_occ, cores)
+        rate = probe_ws / probe_dt
+        sweeps = int(max(4, round(args.cpu_baseline_seconds * rate / cores / n_occ))) * n_occ
+        ws, dt, e_cpu, _ = cpu_walker_sweeps(ham, kup, kdn, args.seed, sweeps, cores)
+        cpu = {"value": ws / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} walkers (one per core) x {sweeps} sweeps, ComplexF64 oracle, {dt:.1f} s", "E_per_site": e_cpu}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.lattice, nw), "sweeps_per_step": n_occ, "walkers_total": total_walkers,
+                       "l2": "inputs_exceed_l2 (W working set %.1f GB per GPU)" % (nw * ns * ns * 8 / 1e9),
+                       "thermalization_sweeps": therm, "rng": "Xoshiro256++ per walker on device"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "observables": {"E_per_site": res["energy"], "acc": res["acc"], "n_OL": res["n_OL"], "n_singular": res["n_singular"]},
+            "kernel_ms": {k: round(v["ms"], 3) for k, v in tm.items()},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

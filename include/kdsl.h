@@ -201,6 +201,14 @@ int kdsl_reset_timers(kdsl_handle h);
  * "update_ctas_per_sm", "inverse_variant", "gemm_variant"}.  KDSL_ERR_INVALID_ARGUMENT if unknown. */
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);
 
+/*
+ * Device-side stopwatch on the engine's stream: kdsl_event_record(h, slot) enqueues a CUDA event
+ * (slot in 0..15); kdsl_event_elapsed returns the milliseconds between two recorded slots after
+ * synchronising on the later one.  Used by bench.py to time whole steps on the device.
+ */
+int kdsl_event_record(kdsl_handle h, int slot);
+int kdsl_event_elapsed(kdsl_handle h, int slot_start, int slot_stop, double *ms);
+
 /* Block until all device work of this handle is complete; returns the first deferred error */
 int kdsl_synchronize(kdsl_handle h);
 

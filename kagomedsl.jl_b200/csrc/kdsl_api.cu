@@ -15,6 +15,7 @@
 #include "kdsl_measure.cuh"
 #include "kdsl_propose.cuh"
 #include "kdsl_refresh.cuh"
+#include "kdsl_refresh_fast.cuh"
 #include "kdsl_update.cuh"
 
 #define KDSL_VERSION_NUM 100
@@ -53,6 +54,8 @@ struct kdsl_handle_s {
     // refresh workspace (tilde_U / inverse), sized for all walkers
     double *A_up = nullptr, *A_dn = nullptr;
     int *status = nullptr;
+    int *colsrc = nullptr;        // [nw][2][Np] column map of the pivoted inverse
+    int Np_up = 0, Np_dn = 0;     // tilde_U dimensions padded to a multiple of 8
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
     double *d_acc8 = nullptr;     // [8]
@@ -75,6 +78,7 @@ struct kdsl_handle_s {
     std::vector<cudaEvent_t> ev_pool;
     double t_ms[KDSL_N_TIMERS] = {0};
     int64_t t_launch[KDSL_N_TIMERS] = {0};
+    cudaEvent_t user_ev[16] = {nullptr};
 };
 
 namespace {
@@ -158,30 +162,68 @@ int launch_update(kdsl_handle h, int parity) {
     return KDSL_OK;
 }
 
+template <int NB, int RPT>
+int launch_inverse_blocked(kdsl_handle h, const int *list, double *A, int spin, int Np) {
+    const size_t smem = ((size_t)2 * Np * NB + NB * NB + 2 * NB + 8) * sizeof(double) +
+                        ((size_t)8 + Np + 5 * NB) * sizeof(int);
+    static bool attr_set[2] = {false, false};
+    (void)attr_set;
+    CK(cudaFuncSetAttribute(k_inverse_blocked<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_blocked<NB, RPT><<<h->S.nw, 256, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np);
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
+int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
+    if (Np <= 256) return launch_inverse_blocked<24, 1>(h, list, A, spin, Np);
+    if (Np <= 512) return launch_inverse_blocked<16, 2>(h, list, A, spin, Np);
+    if (Np <= 1024) return launch_inverse_blocked<8, 4>(h, list, A, spin, Np);
+    return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
+}
+
 // reevaluateW! for the walkers in `list` (device list with device count cnt[2]) or all (list = null)
 int launch_refresh(kdsl_handle h, const int *list) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
+    const bool fast = h->inverse_variant == 0;
     {
         Span sp(h, KDSL_T_REFRESH_GATHER);
-        k_gather_tilde<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+        if (fast)
+            k_gather_tilde_padded<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->Np_up, h->Np_dn);
+        else
+            k_gather_tilde<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
         CK(cudaGetLastError());
     }
     {
         Span sp(h, KDSL_T_REFRESH_INVERSE);
-        const size_t smem = (size_t)Nmax * (2 * sizeof(double) + sizeof(int));
-        k_inverse_gj<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_up, 0, h->status);
-        CK(cudaGetLastError());
-        k_inverse_gj<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_dn, 1, h->status);
-        CK(cudaGetLastError());
+        if (fast) {
+            int rc = launch_inverse(h, list, h->A_up, 0, h->Np_up);
+            if (rc) return rc;
+            rc = launch_inverse(h, list, h->A_dn, 1, h->Np_dn);
+            if (rc) return rc;
+        } else {
+            const size_t smem = (size_t)Nmax * (2 * sizeof(double) + sizeof(int));
+            k_inverse_gj<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_up, 0, h->status);
+            CK(cudaGetLastError());
+            k_inverse_gj<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_dn, 1, h->status);
+            CK(cudaGetLastError());
+        }
         k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
         CK(cudaGetLastError());
     }
     {
         Span sp(h, KDSL_T_REFRESH_GEMM);
-        constexpr int BM = 64, BN = 64;
-        const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
-        k_gemm_W_simt<BM, BN, 16><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+        if (fast) {
+            constexpr int KT = 24;
+            const int tiles = ((S.ns + 71) / 72) * ((Nmax + 71) / 72);
+            const size_t smem = (size_t)4 * 72 * KT * sizeof(double);
+            CK(cudaFuncSetAttribute(k_gemm_W_dmma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn);
+        } else {
+            constexpr int BM = 64, BN = 64;
+            const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
+            k_gemm_W_simt<BM, BN, 16><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+        }
         CK(cudaGetLastError());
     }
     return KDSL_OK;
@@ -372,7 +414,9 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     ALLOC(S.acc_list, 2 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
     ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
     ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 1);
-    ALLOC(h->A_up, nw * n_up * n_up); ALLOC(h->A_dn, nw * n_dn * n_dn);
+    h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
+    ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
+    ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
     ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
 #undef ALLOC
     // default xoshiro states must not be all-zero: seed walker w with a fixed SplitMix64 stream
@@ -399,6 +443,7 @@ int kdsl_destroy(kdsl_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    for (auto e : h->user_ev) if (e) cudaEventDestroy(e);
     for (void *p : h->allocs) cudaFree(p);
     if (h->rp_r) { cudaFree(h->rp_r); cudaFree(h->rp_bond); cudaFree(h->rp_pick); }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -749,6 +794,27 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     } else if (n == "inverse_variant") h->inverse_variant = (int)value;
     else if (n == "gemm_variant") h->gemm_variant = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
+    return KDSL_OK;
+}
+
+int kdsl_event_record(kdsl_handle h, int slot) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= 16) return fail(KDSL_ERR_INVALID_ARGUMENT, "event slot must be in 0..15");
+    if (!h->user_ev[slot]) CK(cudaEventCreate(&h->user_ev[slot]));
+    CK(cudaEventRecord(h->user_ev[slot], h->stream));
+    return KDSL_OK;
+}
+
+int kdsl_event_elapsed(kdsl_handle h, int a, int b, double *ms) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!ms || a < 0 || a >= 16 || b < 0 || b >= 16 || !h->user_ev[a] || !h->user_ev[b])
+        return fail(KDSL_ERR_INVALID_ARGUMENT, "event slots not recorded");
+    CK(cudaEventSynchronize(h->user_ev[b]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->user_ev[a], h->user_ev[b]));
+    *ms = f;
     return KDSL_OK;
 }
 

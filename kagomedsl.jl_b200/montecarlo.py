@@ -286,6 +286,14 @@ class Engine:
     def synchronize(self):
         check(self._L.kdsl_synchronize(self._h))
 
+    def event_record(self, slot: int):
+        check(self._L.kdsl_event_record(self._h, int(slot)))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double(0.0)
+        check(self._L.kdsl_event_elapsed(self._h, int(a), int(b), C.byref(ms)))
+        return ms.value
+
 
 # ------------------------------------------------------------------------------------------
 # Carlo.jl stand-ins (the real Carlo package is the reference's external scheduler)

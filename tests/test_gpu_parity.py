@@ -47,6 +47,24 @@ def test_refresh_matches_oracle(kd, n1, n2, PBC, anti, flux):
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_refresh_imbalanced_filling_and_variants(kd, variant):
+    """N_up != N_down (scripts/FP.jl), N not a multiple of 8; blocked DMMA inverse (0) and simple kernels (1)"""
+    lat, ham = U.problem(4, 3, N_up=20)
+    ns, nw = kd.ns(lat), 5
+    rng = np.random.default_rng(21)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
+    eng = kd.Engine(ham, nw)
+    eng.set_option("inverse_variant", variant)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+    eng.close()
+
+
 def test_update_W_matches_oracle_and_formula(kd):
     lat, ham = U.problem(4, 3)
     ns, nw = kd.ns(lat), 5
@@ -85,9 +103,10 @@ def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps):
     PBC, anti = ((False, False), (False, False)) if n1 == 2 else ((True, True), (True, False))
     lat, ham = U.problem(n1, n2, PBC, anti)
     ns = kd.ns(lat)
-    ku0, kd0 = kd.init_conf_qr(ham, ns, ham.N_up)
-    ku = np.tile(ku0, (nw, 1)); kdn = np.tile(kd0, (nw, 1))
     rng = np.random.default_rng(2024 + n1)
+    # (the reference's QR start state is numerically singular for spin-down on the 12-site lattice,
+    #  so parity runs start from well-conditioned random Mott states, one per walker)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=200.0)
     nb = len(ham.nn)
     r = rng.random((n_sweeps, nw))
     bond = rng.integers(1, nb + 1, size=(n_sweeps, nw)).astype(np.int32)
@@ -128,7 +147,8 @@ def test_device_rng_matches_xoshiro_stream(kd):
     trajectory and same final generator state as the oracle fed with the same initial states"""
     lat, ham = U.problem(4, 3)
     ns, nw, n = kd.ns(lat), 8, 3000
-    ku0, kd0 = kd.init_conf_qr(ham, ns, ham.N_up)
+    ku0, kd0 = U.well_conditioned_mott(np.random.default_rng(8), ham, ns, ham.N_up, 1, cond_max=200.0)
+    ku0, kd0 = ku0[0], kd0[0]
     states = kd.walker_states(1234, nw)
     eng = kd.Engine(ham, nw)
     eng.set_config(ku0, kd0)
