@@ -169,7 +169,7 @@ int launch_inverse_blocked(kdsl_handle h, const int *list, double *A, int spin, 
     static bool attr_set[2] = {false, false};
     (void)attr_set;
     CK(cudaFuncSetAttribute(k_inverse_blocked<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_inverse_blocked<NB, RPT><<<h->S.nw, 256, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np);
+    k_inverse_blocked<NB, RPT><<<h->S.nw, 256, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
     CK(cudaGetLastError());
     return KDSL_OK;
 }
@@ -218,7 +218,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
             const int tiles = ((S.ns + 71) / 72) * ((Nmax + 71) / 72);
             const size_t smem = (size_t)4 * 72 * KT * sizeof(double);
             CK(cudaFuncSetAttribute(k_gemm_W_dmma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn);
+            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn));
         } else {
             constexpr int BM = 64, BN = 64;
             const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);

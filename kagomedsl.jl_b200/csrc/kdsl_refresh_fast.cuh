@@ -58,7 +58,7 @@ k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restri
 template <int NB, int RPT>
 __global__ void __launch_bounds__(256, (RPT == 1 ? 2 : 1))
 k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
-                  int *__restrict__ status, int *__restrict__ colsrc_base, int Np) {
+                  int *__restrict__ status, int *__restrict__ colsrc_base, int Np, int cs_stride) {
     constexpr int T = 256;
     extern __shared__ double sm[];
     const int b = blockIdx.x;
@@ -321,7 +321,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
         __syncthreads();
     }
     // ---- 7. inv(A) = R * P: record which stored column of R is each column of the inverse ----
-    int *colsrc = colsrc_base + ((size_t)2 * b + spin) * Np;
+    int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
     int *sC = reinterpret_cast<int *>(sL);
     for (int j = tid; j < Np; j += T) sC[j] = j;
     __syncthreads();
@@ -341,7 +341,7 @@ template <int KT>
 __global__ void __launch_bounds__(288)
 k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict__ X_up,
               const double *__restrict__ X_dn, const int *__restrict__ status,
-              const int *__restrict__ colsrc_base, int Np_up, int Np_dn) {
+              const int *__restrict__ colsrc_base, int Np_up, int Np_dn, int cs_stride) {
     constexpr int TM = 72, TN = 72, NT = 288;
     extern __shared__ double gsm[];
     double (*sA)[TM * KT] = reinterpret_cast<double (*)[TM * KT]>(gsm);
@@ -358,7 +358,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     if (n0 >= N) return;
     const double *U = spin ? S.U_dn : S.U_up;
     const double *X = (spin ? X_dn : X_up) + (size_t)b * Np * Np;
-    const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * Np;
+    const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
     double *W = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % 3, wn = warp / 3;
