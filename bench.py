@@ -101,7 +101,7 @@ def run_reference(args):
     from oracle import oracle as O
     O.build()
     bonds = np.asarray(ham.nn, dtype=np.int32)
-    bins_per_step = 8          # one reference step: every core advances its walker by 8 bins (8*n_occ sweeps)
+    bins_per_step = 16         # one reference step: every core advances its walker by 16 bins (16*n_occ sweeps)
     sweeps = bins_per_step * n_occ
     mcs = []
     for t in range(cores):
