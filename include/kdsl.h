@@ -190,15 +190,18 @@ int kdsl_get_flags(kdsl_handle h, int32_t *flags);
  * Device-time profile.  kdsl_set_profiling(h, 1) brackets every kernel launch with CUDA events on
  * the engine's stream; kdsl_timers then returns, per kernel class, the summed device
  * milliseconds (ms[KDSL_N_TIMERS]) and launch counts (launches[KDSL_N_TIMERS]) since the last
- * kdsl_reset_timers, plus (any may be NULL) the number of accepted moves the W-update launches
- * processed.  Launch counts are maintained even when profiling is off.
+ * kdsl_reset_timers, plus (any may be NULL) update_counts[2]: [0] accepted moves streamed by the
+ * rank-1 W-update launches (update_variant 0), [1] walker flushes W0 += A B^T executed by the delayed
+ * update launches (update_variant 1).  Launch counts are maintained even when profiling is off.
  */
 int kdsl_set_profiling(kdsl_handle h, int enabled);
-int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_moves);
+int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_counts);
 int kdsl_reset_timers(kdsl_handle h);
 
-/* Tunables: name in {"refresh_every" (0 = reference cadence n_occ), "update_variant",
- * "update_ctas_per_sm", "inverse_variant", "gemm_variant"}.  KDSL_ERR_INVALID_ARGUMENT if unknown. */
+/* Tunables: "refresh_every" (0 = reference cadence n_occ); "update_variant" (1 = delayed rank-k
+ * updates, default; 0 = the reference's immediate rank-1 update streamed per accepted move);
+ * "update_ctas_per_sm", "update_cols_per_item" (rank-1 kernel tiling); "inverse_variant" / "gemm_variant"
+ * (0 = blocked DMMA kernels, 1 = simple cross-check kernels).  KDSL_ERR_INVALID_ARGUMENT if unknown. */
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);
 
 /*

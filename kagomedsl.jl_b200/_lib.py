@@ -91,7 +91,7 @@ def lib():
         L.kdsl_get_Z.argtypes = [vp, vp, vp]
         L.kdsl_get_flags.argtypes = [vp, vp]
         L.kdsl_set_profiling.argtypes = [vp, i32]
-        L.kdsl_timers.argtypes = [vp, vp, vp, C.POINTER(i64)]
+        L.kdsl_timers.argtypes = [vp, vp, vp, vp]
         L.kdsl_reset_timers.argtypes = [vp]
         L.kdsl_set_option.argtypes = [vp, C.c_char_p, i64]
         L.kdsl_synchronize.argtypes = [vp]

@@ -16,9 +16,13 @@
 #include "kdsl_propose.cuh"
 #include "kdsl_refresh.cuh"
 #include "kdsl_refresh_fast.cuh"
+#include "kdsl_delayed.cuh"
 #include "kdsl_update.cuh"
 
-#define KDSL_VERSION_NUM 100
+#define KDSL_VERSION_NUM 110
+#define KDSL_KTH 16          /* pending factors that trigger a flush */
+#define KDSL_FLUSH_EVERY 4   /* sweeps between flush launches    */
+#define KDSL_KMAX (KDSL_KTH + KDSL_FLUSH_EVERY)
 
 static thread_local std::string g_err;
 
@@ -70,7 +74,8 @@ struct kdsl_handle_s {
     int64_t walker_sweeps = 0;
     // options
     int64_t refresh_every = 0;
-    int update_variant = 0, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
+    int update_variant = 1, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
+    int since_flush = 0;
     int update_ch = 8;
     // profiling
     bool profiling = false;
@@ -229,6 +234,29 @@ int launch_refresh(kdsl_handle h, const int *list) {
     return KDSL_OK;
 }
 
+// W0 += pending factors for the listed walkers (list = device list with count cnt[4]) or for all walkers
+int launch_flush(kdsl_handle h, bool all) {
+    const DevState &S = h->S;
+    const int Nmax = std::max(S.n_up, S.n_dn);
+    const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KDSL_KMAX * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    {
+        Span sp(h, KDSL_T_UPDATE);
+        k_flush<KDSL_KMAX><<<h->num_sms * 4, 288, smem, h->stream>>>(S, all ? nullptr : S.flush_list, all ? nullptr : S.cnt + 4, S.nw);
+        CK(cudaGetLastError());
+        k_flush_done<<<8, 256, 0, h->stream>>>(S, all ? nullptr : S.flush_list, all ? nullptr : S.cnt + 4, S.nw);
+        CK(cudaGetLastError());
+        k_zero_int<<<1, 1, 0, h->stream>>>(S.cnt + 4);
+        CK(cudaGetLastError());
+    }
+    h->since_flush = 0;
+    return KDSL_OK;
+}
+
 int ensure_replay_capacity(kdsl_handle h, size_t n) {
     if (n <= h->rp_cap) return KDSL_OK;
     if (h->rp_r) { cudaFree(h->rp_r); cudaFree(h->rp_bond); cudaFree(h->rp_pick); }
@@ -247,10 +275,17 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
     const int pgrid = grid_for_warps(S.nw);
     for (int64_t s = 0; s < n; s++) {
         const bool gate = (h->sweeps % period) == 0;            // src/MonteCarlo.jl:595 (pre-increment)
+        const bool delayed = h->update_variant == 1;
         {
             Span sp(h, KDSL_T_PROPOSE);
-            if (replay) {
-                const size_t off = (size_t)s * S.nw;
+            const size_t off = (size_t)s * S.nw;
+            if (delayed) {
+                if (replay)
+                    k_propose_delayed<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
+                                                                          have_pick ? h->rp_pick + off : nullptr);
+                else
+                    k_propose_delayed<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, nullptr, nullptr, nullptr);
+            } else if (replay) {
                 k_propose<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
                                                               h->rp_bond + off, have_pick ? h->rp_pick + off : nullptr);
             } else {
@@ -258,20 +293,25 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             }
             CK(cudaGetLastError());
         }
-        if (!gate) {
-            int rc = launch_update(h, h->parity);
-            if (rc) return rc;
-            h->parity ^= 1;
-        } else {
+        if (gate) {
             int rc = launch_refresh(h, S.ref_list);
             if (rc) return rc;
             CK(cudaMemsetAsync(S.cnt + 2, 0, sizeof(int), h->stream));
+        } else if (!delayed) {
+            int rc = launch_update(h, h->parity);
+            if (rc) return rc;
+            h->parity ^= 1;
+        }
+        if (delayed && ++h->since_flush >= KDSL_FLUSH_EVERY) {
+            int rc = launch_flush(h, false);
+            if (rc) return rc;
         }
         h->sweeps += 1;                                          // Carlo: ctx.sweeps += 1
         h->walker_sweeps += S.nw;
         if (therm >= 0 && h->sweeps > therm && (h->sweeps % S.n_occ) == 0) {   // :630 (post-increment)
             Span sp(h, KDSL_T_MEASURE);
-            k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
+            if (delayed) k_measure_delayed<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
+            else k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             CK(cudaGetLastError());
         }
         if (h->profiling && h->spans.size() > 16384) {
@@ -413,7 +453,11 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     ALLOC(S.trow_up, nw * n_up); ALLOC(S.trow_dn, nw * n_dn);
     ALLOC(S.acc_list, 2 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
     ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
-    ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 1);
+    ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 4);
+    S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;
+    ALLOC(S.facA_up, nw * S.kmax * ns); ALLOC(S.facA_dn, nw * S.kmax * ns);
+    ALLOC(S.facB_up, nw * S.kmax * n_up); ALLOC(S.facB_dn, nw * S.kmax * n_dn);
+    ALLOC(S.fcnt, nw); ALLOC(S.flush_list, nw);
     h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
     ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
@@ -497,8 +541,10 @@ int kdsl_set_config(kdsl_handle h, const int32_t *kup, const int32_t *kdn) {
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(S.cnt, 0, 8 * sizeof(int), h->stream));
     CK(cudaMemsetAsync(S.flags, 0, (size_t)S.nw * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(S.fcnt, 0, (size_t)S.nw * sizeof(int), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->parity = 0;
+    h->since_flush = 0;
     h->have_config = true;
     h->W_valid = false;
     return KDSL_OK;
@@ -597,7 +643,7 @@ int kdsl_measure(kdsl_handle h, double *ol) {
     const DevState &S = h->S;
     {
         Span sp(h, KDSL_T_MEASURE);
-        k_measure<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+        k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(ol, h->d_tmp_d, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -672,6 +718,7 @@ int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     if (!out || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / out");
     const int N = spin ? S.n_dn : S.n_up;
     const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
+    if ((rc = launch_flush(h, true))) return rc;           // fold pending delayed factors into W0
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double), cudaMemcpyDeviceToHost));
     return KDSL_OK;
@@ -684,6 +731,7 @@ int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
     if (!in || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / in");
     const int N = spin ? S.n_dn : S.n_up;
     double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
+    if ((rc = launch_flush(h, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double), cudaMemcpyHostToDevice));
     return KDSL_OK;
@@ -707,6 +755,7 @@ int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32
         mv[m] = walker[m]; mv[n_moves + m] = l_up[m]; mv[2 * (size_t)n_moves + m] = K_up[m];
         mv[3 * (size_t)n_moves + m] = l_dn[m]; mv[4 * (size_t)n_moves + m] = K_dn[m];
     }
+    if ((rc = launch_flush(h, true))) return rc;
     int *d_mv = nullptr;
     CK(cudaMalloc(&d_mv, mv.size() * sizeof(int)));
     CK(cudaMemcpyAsync(d_mv, mv.data(), mv.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -763,9 +812,10 @@ int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_mo
     if (ms) memcpy(ms, h->t_ms, sizeof h->t_ms);
     if (launches) memcpy(launches, h->t_launch, sizeof h->t_launch);
     if (update_moves) {
-        unsigned long long v = 0;
-        CK(cudaMemcpy(&v, h->S.upd_moves, sizeof v, cudaMemcpyDeviceToHost));
-        *update_moves = (int64_t)v;
+        unsigned long long v[2] = {0, 0};
+        CK(cudaMemcpy(v, h->S.upd_moves, sizeof v, cudaMemcpyDeviceToHost));
+        update_moves[0] = (int64_t)v[0];
+        update_moves[1] = (int64_t)v[1];
     }
     return KDSL_OK;
 }
@@ -776,7 +826,7 @@ int kdsl_reset_timers(kdsl_handle h) {
     if ((rc = flush_spans(h))) return rc;
     memset(h->t_ms, 0, sizeof h->t_ms);
     memset(h->t_launch, 0, sizeof h->t_launch);
-    CK(cudaMemset(h->S.upd_moves, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(h->S.upd_moves, 0, 4 * sizeof(unsigned long long)));
     return KDSL_OK;
 }
 
@@ -786,7 +836,15 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (n == "refresh_every") {
         if (value < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "refresh_every must be >= 0");
         h->refresh_every = value;
-    } else if (n == "update_variant") h->update_variant = (int)value;
+    } else if (n == "update_variant") {
+        if (value != 0 && value != 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming) or 1 (delayed rank-k)");
+        if (h->have_config && h->W_valid) {
+            int rc = use_device(h);
+            if (rc) return rc;
+            if ((rc = launch_flush(h, true))) return rc;
+        }
+        h->update_variant = (int)value;
+    }
     else if (n == "update_ctas_per_sm") h->update_ctas_per_sm = (int)value;
     else if (n == "update_cols_per_item") {
         if (value < 1 || value > 4096) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_cols_per_item out of range");

@@ -33,7 +33,13 @@ struct DevState {
     unsigned long long *n_refresh;  // [nw]
     double *ol_sum, *ol_sq, *ol_last;  // [nw]
     unsigned long long *ol_n;    // [nw]
-    unsigned long long *upd_moves;  // [1] accepted moves streamed by the W-update launches
+    unsigned long long *upd_moves;  // [0] accepted moves streamed by the rank-1 launches, [1] walkers flushed (delayed mode)
+    // delayed (rank-k) updates: W = W0 + sum_{m<fcnt} A_m (x) B_m
+    double *facA_up, *facA_dn;   // [nw][kmax][ns]
+    double *facB_up, *facB_dn;   // [nw][kmax][N]
+    int *fcnt;                   // [nw] pending factors per walker
+    int *flush_list;             // [nw] walkers that reached kth pending factors (count in cnt[4])
+    int kmax, kth;
 };
 
 __device__ __forceinline__ unsigned long long rotl64(unsigned long long x, int k) {

@@ -271,10 +271,11 @@ class Engine:
     def timers(self) -> Dict[str, Dict[str, float]]:
         ms = np.zeros(_lib.N_TIMERS)
         n = np.zeros(_lib.N_TIMERS, dtype=np.int64)
-        mv = C.c_int64(0)
-        check(self._L.kdsl_timers(self._h, _ptr(ms), _ptr(n), C.byref(mv)))
+        mv = np.zeros(2, dtype=np.int64)
+        check(self._L.kdsl_timers(self._h, _ptr(ms), _ptr(n), _ptr(mv)))
         out = {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(_lib.TIMER_NAMES)}
-        out["update"]["moves"] = int(mv.value)
+        out["update"]["moves"] = int(mv[0])
+        out["update"]["flushes"] = int(mv[1])
         return out
 
     def reset_timers(self):

@@ -97,9 +97,11 @@ def test_update_W_matches_oracle_and_formula(kd):
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("n1,n2,nw,n_sweeps", [(2, 2, 8, 600), (4, 3, 8, 1500), (6, 6, 6, 2500)])
-def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps):
-    """replayed (r, bond) sequence: kappa, Z, acceptance counters bit-exact; W within 1e-10"""
+def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps, variant):
+    """replayed (r, bond) sequence: kappa, Z, acceptance counters bit-exact; W within 1e-10.
+    variant 1 = delayed rank-k updates (default), 0 = immediate rank-1 update like the reference"""
     PBC, anti = ((False, False), (False, False)) if n1 == 2 else ((True, True), (True, False))
     lat, ham = U.problem(n1, n2, PBC, anti)
     ns = kd.ns(lat)
@@ -111,6 +113,7 @@ def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps):
     r = rng.random((n_sweeps, nw))
     bond = rng.integers(1, nb + 1, size=(n_sweeps, nw)).astype(np.int32)
     eng = kd.Engine(ham, nw)
+    eng.set_option("update_variant", variant)
     eng.set_config(ku, kdn)
     eng.refresh()
     orc = U.oracle_walkers(ham, ku, kdn)
@@ -142,7 +145,8 @@ def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps):
     eng.close()
 
 
-def test_device_rng_matches_xoshiro_stream(kd):
+@pytest.mark.parametrize("variant", [1, 0])
+def test_device_rng_matches_xoshiro_stream(kd, variant):
     """device-drawn random numbers follow Julia's Xoshiro256++ conventions: same
     trajectory and same final generator state as the oracle fed with the same initial states"""
     lat, ham = U.problem(4, 3)
@@ -151,6 +155,7 @@ def test_device_rng_matches_xoshiro_stream(kd):
     ku0, kd0 = ku0[0], kd0[0]
     states = kd.walker_states(1234, nw)
     eng = kd.Engine(ham, nw)
+    eng.set_option("update_variant", variant)
     eng.set_config(ku0, kd0)
     eng.set_rng(states)
     eng.refresh()
@@ -187,6 +192,33 @@ def test_measure_matches_oracle_getOL(kd):
     for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
         ref = mc.getOL()
         assert abs(ol[w] - ref) <= TOL * max(1.0, abs(ref))
+    eng.close()
+
+
+def test_measure_with_pending_factors(kd):
+    """O_L evaluated from W0 + pending delayed factors equals the oracle's O_L on the same trajectory"""
+    lat, ham = U.problem(4, 3)
+    ns, nw, n = kd.ns(lat), 8, 17                      # 17 sweeps: no refresh since sweep 0, factors pending
+    rng = np.random.default_rng(77)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=200.0)
+    r = rng.random((n, nw)) * 0.3                       # small r: many acceptances
+    bond = rng.integers(1, len(ham.nn) + 1, size=(n, nw)).astype(np.int32)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    eng.sweeps = 1
+    eng.replay(r, bond)
+    ol = eng.measure()
+    orc = U.oracle_walkers(ham, ku, kdn)
+    n_acc = 0
+    for w, mc in enumerate(orc):
+        mc.sweeps = 1
+        for s in range(n):
+            n_acc += mc.sweep(replay=(r[s, w], int(bond[s, w]), 1)) & 1
+            mc.sweeps = mc.sweeps + 1
+        ref = mc.getOL()
+        assert abs(ol[w] - ref) <= TOL * max(1.0, abs(ref))
+    assert n_acc > nw                                   # the test really exercised pending factors
     eng.close()
 
 

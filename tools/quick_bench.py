@@ -53,8 +53,10 @@ def main():
         "acc": acc[1] / acc[0], "E_site": acc[2] / max(acc[4], 1) / ns, "n_OL": acc[4], "n_refresh": acc[6], "n_singular": acc[7],
         "timers": tm,
         "update_GBs": upd["moves"] * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
+        "flush_GBs": upd["flushes"] * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
     }, indent=1))
     # pure W-update bandwidth: every walker gets one move
+    eng.set_profiling(True)
     z = np.arange(args.walkers, dtype=np.int32)
     one = np.ones(args.walkers, dtype=np.int32)
     eng.reset_timers()
