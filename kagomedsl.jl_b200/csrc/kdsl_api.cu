@@ -281,10 +281,10 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             const size_t off = (size_t)s * S.nw;
             if (delayed) {
                 if (replay)
-                    k_propose_delayed<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
+                    k_propose_delayed<true><<<S.nw, 128, 0, h->stream>>>(S, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
                                                                           have_pick ? h->rp_pick + off : nullptr);
                 else
-                    k_propose_delayed<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, nullptr, nullptr, nullptr);
+                    k_propose_delayed<false><<<S.nw, 128, 0, h->stream>>>(S, gate ? 1 : 0, nullptr, nullptr, nullptr);
             } else if (replay) {
                 k_propose<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
                                                               h->rp_bond + off, have_pick ? h->rp_pick + off : nullptr);
