@@ -241,7 +241,7 @@ def run_ours(args):
     total_walkers = nw * world
     value = total_walkers * n_occ * K / (ms * 1e-3)
     launches = sum(v["launches"] for v in tm.values())
-    B_acc = 16 * ns * ns                                 # algorithmic bytes per accepted move
+    B_acc = 16 * ns * ns                                 # bytes to read+write both W matrices of a walker once
     upd = tm["update"]
     peaks = {}
     try:
@@ -249,19 +249,38 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = upd["moves"] * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_update (Sherman-Morrison rank-1 W update)", "achieved": achieved, "peak": peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "moves_per_launch": upd["moves"] / max(upd["launches"], 1), "algorithmic_bytes_per_move": B_acc,
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"
+    # The HBM-bound W update of the production path: k_flush folds the >= 16 pending rank-1 factors of a walker
+    # into W with ONE read+write pass (delayed Sherman-Morrison).  Algorithmic bytes per launch = walkers
+    # flushed x 16 ns^2; the reference's immediate rank-1 update would move 16 ns^2 per ACCEPTED move.
+    n_flush = upd.get("flushes", 0)
+    achieved = n_flush * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else 0.0
+    moves_total = res["sum_acc"] / world                 # accepted moves on this rank (all folded by flush or refresh)
+    roofline = {"bound": "hbm", "kernel": "k_flush (delayed rank-k Sherman-Morrison update of W, DMMA)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "walkers_flushed_per_launch": n_flush / max(upd["launches"], 1), "algorithmic_bytes_per_flush": B_acc,
                 "avg_launch_us": 1e3 * upd["ms"] / max(upd["launches"], 1),
-                "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None}
+                "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None,
+                "rank1_equivalent_GBs": moves_total * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
+                "note": "rank1_equivalent = accepted moves x 16 ns^2 / flush time, i.e. the traffic the reference's per-move update would need"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("k_update_dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(prof)).get("k_flush_dram_bytes_per_launch")
         except Exception:
             pass
+    # FP64 tensor-pipe roofline of the W re-evaluation (batched inverse + GEMM), the other heavy kernels
+    dmma_peak = eng.fp64_dmma_peak_tflops()
+    n_refresh = res["n_refresh"] / world
+    Nh = ns // 2
+    flop_refresh = 2.0 * (2.0 * Nh ** 3 + 2.0 * ns * Nh ** 2)      # inverse + U*X for both species
+    t_ref = (tm["refresh_inverse"]["ms"] + tm["refresh_gemm"]["ms"]) * 1e-3
+    roofline_refresh = {"bound": "tensor", "kernel": "k_inverse_blocked + k_gemm_W_dmma (FP64 DMMA)",
+                        "achieved": n_refresh * flop_refresh / t_ref / 1e12 if t_ref > 0 else 0.0, "peak": dmma_peak,
+                        "peak_source": "measured in this run by kdsl_bench_fp64_dmma (MEASURED_PEAKS.json has no FP64 figure)",
+                        "unit": "TFLOP/s", "frac": (n_refresh * flop_refresh / t_ref / 1e12 / dmma_peak) if t_ref > 0 and dmma_peak > 0 else None,
+                        "algorithmic_flop_per_walker_refresh": flop_refresh, "walker_refreshes": n_refresh,
+                        "kernel_share_of_step": (tm["refresh_inverse"]["ms"] + tm["refresh_gemm"]["ms"]) / ms if ms > 0 else None}
 
     # ---- e2e: same work through the public API with HOST buffers (replayed proposal stream) ----
     e2e = None
@@ -288,6 +307,23 @@ def run_ours(args):
                "h2d_bytes_per_step": int(n_occ * nw * (8 + 4)), "d2h_bytes_per_step": int(nw * 16 + 64),
                "mode": "kdsl_replay: host supplies (r, bond) for every proposal from pinned memory; O_L and counters copied back"}
 
+    # ---- the reference-style immediate rank-1 W update (update_W!, src/MonteCarlo.jl:279-292) timed alone:
+    #      every walker applies one move; 16 ns^2 algorithmic bytes per move, W working set >> L2 ----
+    eng.set_option("update_variant", 0)
+    eng.reset_timers()
+    eng.set_profiling(True)
+    wl = np.arange(nw, dtype=np.int32)
+    one = np.ones(nw, dtype=np.int32)
+    for rep in range(4):
+        eng.update_W(wl, one * (1 + rep), one * (3 + rep), one * (2 + rep), one * (5 + rep))
+    t1 = eng.timers()["update"]
+    eng.set_profiling(False)
+    r1 = t1["moves"] * B_acc / (t1["ms"] * 1e-3) / 1e9 if t1["ms"] > 0 else 0.0
+    roofline_rank1 = {"bound": "hbm", "kernel": "k_update_ldg (immediate rank-1 update, one move per walker, timed alone)",
+                      "achieved": r1, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": r1 / peak,
+                      "moves_per_launch": t1["moves"] / max(t1["launches"], 1), "algorithmic_bytes_per_move": B_acc}
+    eng.set_option("update_variant", 1)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
@@ -307,8 +343,10 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.lattice, nw), "sweeps_per_step": n_occ, "walkers_total": total_walkers,
                        "l2": "inputs_exceed_l2 (W working set %.1f GB per GPU)" % (nw * ns * ns * 8 / 1e9),
-                       "thermalization_sweeps": therm, "rng": "Xoshiro256++ per walker on device"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                       "thermalization_sweeps": therm, "rng": "Xoshiro256++ per walker on device",
+                       "w_update": "delayed rank-k (flush at 16 pending factors); refresh at the reference cadence n_occ"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_refresh": roofline_refresh,
+            "roofline_rank1_update": roofline_rank1, "e2e": e2e, "cpu_baseline": cpu,
             "observables": {"E_per_site": res["energy"], "acc": res["acc"], "n_OL": res["n_OL"], "n_singular": res["n_singular"]},
             "kernel_ms": {k: round(v["ms"], 3) for k, v in tm.items()},
         }

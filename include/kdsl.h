@@ -212,6 +212,10 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);
 int kdsl_event_record(kdsl_handle h, int slot);
 int kdsl_event_elapsed(kdsl_handle h, int slot_start, int slot_stop, double *ms);
 
+/* Measured FP64 tensor-pipe (DMMA m8n8k4) peak of this device in TFLOP/s: the roofline denominator of the
+ * W re-evaluation kernels (MEASURED_PEAKS.json holds no FP64 figure). Runs a ~10 ms register-only probe. */
+int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops);
+
 /* Block until all device work of this handle is complete; returns the first deferred error */
 int kdsl_synchronize(kdsl_handle h);
 

@@ -32,7 +32,7 @@ SYMBOLS = (
     "kdsl_get_sweeps", "kdsl_refresh", "kdsl_sweep", "kdsl_replay", "kdsl_measure", "kdsl_last_OL",
     "kdsl_accumulators", "kdsl_reset_accumulators", "kdsl_get_W", "kdsl_set_W", "kdsl_update_W",
     "kdsl_get_Z", "kdsl_get_flags", "kdsl_set_profiling", "kdsl_timers", "kdsl_reset_timers",
-    "kdsl_set_option", "kdsl_synchronize", "kdsl_info", "kdsl_event_record", "kdsl_event_elapsed",
+    "kdsl_set_option", "kdsl_synchronize", "kdsl_info", "kdsl_event_record", "kdsl_event_elapsed", "kdsl_bench_fp64_dmma",
 )
 
 
@@ -98,6 +98,7 @@ def lib():
         L.kdsl_info.argtypes = [vp, vp]
         L.kdsl_device_count.argtypes = [C.POINTER(i32)]
         L.kdsl_event_record.argtypes = [vp, i32]
+        L.kdsl_bench_fp64_dmma.argtypes = [vp, C.POINTER(C.c_double)]
         L.kdsl_event_elapsed.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
         _lib = L
     return _lib

@@ -76,6 +76,7 @@ struct kdsl_handle_s {
     int64_t refresh_every = 0;
     int update_variant = 1, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
     int since_flush = 0;
+    int inverse_tuning = 0;
     int update_ch = 8;
     // profiling
     bool profiling = false;
@@ -167,22 +168,27 @@ int launch_update(kdsl_handle h, int parity) {
     return KDSL_OK;
 }
 
-template <int NB, int RPT>
+template <int NB, int RPT, int T, int MINB>
 int launch_inverse_blocked(kdsl_handle h, const int *list, double *A, int spin, int Np) {
-    const size_t smem = ((size_t)2 * Np * NB + NB * NB + 2 * NB + 8) * sizeof(double) +
-                        ((size_t)8 + Np + 5 * NB) * sizeof(int);
-    static bool attr_set[2] = {false, false};
-    (void)attr_set;
-    CK(cudaFuncSetAttribute(k_inverse_blocked<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_inverse_blocked<NB, RPT><<<h->S.nw, 256, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    const size_t smem = ((size_t)2 * Np * NB + NB * NB + 2 * NB + T / 32) * sizeof(double) +
+                        ((size_t)T / 32 + Np + 5 * NB) * sizeof(int);
+    CK(cudaFuncSetAttribute(k_inverse_blocked<NB, RPT, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_blocked<NB, RPT, T, MINB><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
     CK(cudaGetLastError());
     return KDSL_OK;
 }
 
+// one CTA per matrix and ONE CTA per SM: 148 x N^2 x 8 B of live matrices stay L2 resident
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
-    if (Np <= 256) return launch_inverse_blocked<24, 1>(h, list, A, spin, Np);
-    if (Np <= 512) return launch_inverse_blocked<16, 2>(h, list, A, spin, Np);
-    if (Np <= 1024) return launch_inverse_blocked<8, 4>(h, list, A, spin, Np);
+    const int v = h->inverse_tuning;
+    if (Np <= 256) {
+        if (v == 1) return launch_inverse_blocked<24, 1, 256, 2>(h, list, A, spin, Np);
+        if (v == 2) return launch_inverse_blocked<16, 2, 128, 4>(h, list, A, spin, Np);
+        if (v == 3) return launch_inverse_blocked<8, 2, 128, 4>(h, list, A, spin, Np);
+        return launch_inverse_blocked<16, 1, 256, 2>(h, list, A, spin, Np);
+    }
+    if (Np <= 512) return launch_inverse_blocked<16, 2, 256, 1>(h, list, A, spin, Np);
+    if (Np <= 1024) return launch_inverse_blocked<8, 4, 256, 1>(h, list, A, spin, Np);
     return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
 }
 
@@ -281,10 +287,15 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             const size_t off = (size_t)s * S.nw;
             if (delayed) {
                 if (replay)
-                    k_propose_delayed<true><<<S.nw, 128, 0, h->stream>>>(S, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
-                                                                          have_pick ? h->rp_pick + off : nullptr);
+                    k_decide<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
+                                                                 have_pick ? h->rp_pick + off : nullptr);
                 else
-                    k_propose_delayed<false><<<S.nw, 128, 0, h->stream>>>(S, gate ? 1 : 0, nullptr, nullptr, nullptr);
+                    k_decide<false><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, nullptr, nullptr, nullptr);
+                CK(cudaGetLastError());
+                if (!gate) {                    // (at a gate sweep nobody is listed: accepted walkers are re-evaluated)
+                    k_build_factors<KDSL_KMAX><<<h->num_sms * 8, 256, 0, h->stream>>>(S, h->parity);
+                    h->parity ^= 1;
+                }
             } else if (replay) {
                 k_propose<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
                                                               h->rp_bond + off, have_pick ? h->rp_pick + off : nullptr);
@@ -356,6 +367,21 @@ k_stage_moves(DevState S, int parity, int n_moves, const int *__restrict__ mv) {
     if (m == 0 && lane == 0) S.cnt[parity] = n_moves;
 }
 
+// FP64 tensor-pipe peak probe: 8 independent DMMA accumulation chains per warp
+__global__ void __launch_bounds__(256) k_dmma_peak(double *sink, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; q++) c[q][0] = c[q][1] = 0.0;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) dmma_8x8x4(c[q][0], c[q][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += c[q][0] + c[q][1];
+    if (s == 123.456) sink[0] = s;
+}
 }  // namespace
 
 extern "C" {
@@ -451,7 +477,7 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     ALLOC(S.W_up, nw * ns * n_up); ALLOC(S.W_dn, nw * ns * n_dn);
     ALLOC(S.col_up, nw * ns); ALLOC(S.col_dn, nw * ns);
     ALLOC(S.trow_up, nw * n_up); ALLOC(S.trow_dn, nw * n_dn);
-    ALLOC(S.acc_list, 2 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
+    ALLOC(S.acc_list, 12 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
     ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
     ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 4);
     S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;
@@ -718,7 +744,7 @@ int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     if (!out || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / out");
     const int N = spin ? S.n_dn : S.n_up;
     const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
-    if ((rc = launch_flush(h, true))) return rc;           // fold pending delayed factors into W0
+    if (h->update_variant == 1 && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double), cudaMemcpyDeviceToHost));
     return KDSL_OK;
@@ -731,7 +757,7 @@ int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
     if (!in || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / in");
     const int N = spin ? S.n_dn : S.n_up;
     double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
-    if ((rc = launch_flush(h, true))) return rc;
+    if (h->update_variant == 1 && (rc = launch_flush(h, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double), cudaMemcpyHostToDevice));
     return KDSL_OK;
@@ -755,7 +781,7 @@ int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32
         mv[m] = walker[m]; mv[n_moves + m] = l_up[m]; mv[2 * (size_t)n_moves + m] = K_up[m];
         mv[3 * (size_t)n_moves + m] = l_dn[m]; mv[4 * (size_t)n_moves + m] = K_dn[m];
     }
-    if ((rc = launch_flush(h, true))) return rc;
+    if (h->update_variant == 1 && (rc = launch_flush(h, true))) return rc;
     int *d_mv = nullptr;
     CK(cudaMalloc(&d_mv, mv.size() * sizeof(int)));
     CK(cudaMemcpyAsync(d_mv, mv.data(), mv.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -843,6 +869,12 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
             if (rc) return rc;
             if ((rc = launch_flush(h, true))) return rc;
         }
+        if (h->have_config) {
+            int rc = use_device(h);
+            if (rc) return rc;
+            CK(cudaMemsetAsync(h->S.cnt, 0, 2 * sizeof(int), h->stream));
+        }
+        h->parity = 0;
         h->update_variant = (int)value;
     }
     else if (n == "update_ctas_per_sm") h->update_ctas_per_sm = (int)value;
@@ -851,6 +883,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         h->update_ch = (int)value;
     } else if (n == "inverse_variant") h->inverse_variant = (int)value;
     else if (n == "gemm_variant") h->gemm_variant = (int)value;
+    else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
     return KDSL_OK;
 }
@@ -873,6 +906,42 @@ int kdsl_event_elapsed(kdsl_handle h, int a, int b, double *ms) {
     float f = 0.f;
     CK(cudaEventElapsedTime(&f, h->user_ev[a], h->user_ev[b]));
     *ms = f;
+    return KDSL_OK;
+}
+
+/* developer hook (not in kdsl.h): cycles of CTA 0 per phase of k_inverse_blocked since the last call */
+int kdsl_debug_inverse_phases(kdsl_handle h, long long *out) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyFromSymbol(out, g_inv_phase_cycles, 8 * sizeof(long long)));
+    long long z[8] = {0};
+    CK(cudaMemcpyToSymbol(g_inv_phase_cycles, z, sizeof z));
+    return KDSL_OK;
+}
+
+int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!tflops) return fail(KDSL_ERR_INVALID_ARGUMENT, "tflops is null");
+    const int iters = 4096, grid = h->num_sms * 8;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(a, h->stream));
+        k_dmma_peak<<<grid, 256, 0, h->stream>>>(h->d_acc8, iters);
+        CK(cudaEventRecord(b, h->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double flops = (double)grid * 8 /*warps*/ * iters * 8 /*chains*/ * 512.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
     return KDSL_OK;
 }
 

@@ -39,162 +39,178 @@ __device__ __forceinline__ double w_entry_thread(const DevState &S, const double
 // append factor number `cnt` for one species with all threads of the CTA:
 //   A_new = W[:, l],  B_new = alpha (W[K, :] - e_l),  alpha = -1 / W[K, l]   (src/MonteCarlo.jl:286-290)
 // s_bl[m] = B_m[l], s_ak[m] = A_m[K] of the pending factors are staged in shared memory by the caller.
-template <int NT>
+// All global loads of an element are issued before its FMA chain (KMX-way memory parallelism).
+template <int NT, int KMX>
 __device__ __forceinline__ void build_factor_cta(const DevState &S, int w, int spin, int K, int l, int cnt,
                                                  const double *s_bl, const double *s_ak, int tid) {
     const int ns = S.ns, N = spin ? S.n_dn : S.n_up;
-    double *A = (spin ? S.facA_dn : S.facA_up) + (size_t)w * S.kmax * ns;
-    double *B = (spin ? S.facB_dn : S.facB_up) + (size_t)w * S.kmax * N;
-    const double *W0 = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
-    double *An = A + (size_t)cnt * ns, *Bn = B + (size_t)cnt * N;
-    const double *W0col = W0 + (size_t)l * ns;
-    for (int i = tid; i < ns; i += NT) {                       // column l of the current W
-        double acc = W0col[i];
-#pragma unroll 4
-        for (int m = 0; m < cnt; m++) acc = fma(A[(size_t)m * ns + i], s_bl[m], acc);
-        An[i] = acc;
-    }
+    double *__restrict__ A = (spin ? S.facA_dn : S.facA_up) + (size_t)w * S.kmax * ns;
+    double *__restrict__ B = (spin ? S.facB_dn : S.facB_up) + (size_t)w * S.kmax * N;
+    const double *__restrict__ W0 = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
+    double *__restrict__ An = A + (size_t)cnt * ns;
+    double *__restrict__ Bn = B + (size_t)cnt * N;
+    const double *__restrict__ W0col = W0 + (size_t)l * ns;
     double piv = W0col[K];                                     // pivot W[K, l], same accumulation order
     for (int m = 0; m < cnt; m++) piv = fma(s_ak[m], s_bl[m], piv);
     const double alpha = -1.0 / piv;
+    for (int i = tid; i < ns; i += NT) {                       // column l of the current W
+        double av[KMX];
+        double acc = W0col[i];
+#pragma unroll
+        for (int m = 0; m < KMX; m++) av[m] = m < cnt ? A[(size_t)m * ns + i] : 0.0;
+#pragma unroll
+        for (int m = 0; m < KMX; m++) if (m < cnt) acc = fma(av[m], s_bl[m], acc);
+        An[i] = acc;
+    }
     for (int j = tid; j < N; j += NT) {                        // row K of the current W
+        double bv[KMX];
         double acc = W0[(size_t)j * ns + K];
-#pragma unroll 4
-        for (int m = 0; m < cnt; m++) acc = fma(s_ak[m], B[(size_t)m * N + j], acc);
+#pragma unroll
+        for (int m = 0; m < KMX; m++) bv[m] = m < cnt ? B[(size_t)m * N + j] : 0.0;
+#pragma unroll
+        for (int m = 0; m < KMX; m++) if (m < cnt) acc = fma(s_ak[m], bv[m], acc);
         if (j == l) acc -= 1.0;
         Bn[j] = alpha * acc;
     }
 }
 
-// Carlo.sweep! proposal (reference src/MonteCarlo.jl:538-607) with delayed W updates.
-// One CTA of 128 threads per walker: warp 0 evaluates the (scalar) Metropolis decision with the
-// reference's exact predicate and RNG consumption order and applies the integer state changes;
-// on acceptance all 4 warps build the new rank-1 factor pair of both species.
+// Carlo.sweep! proposal (reference src/MonteCarlo.jl:538-607) with delayed W updates, split in two
+// short kernels so that every walker's latency chain runs concurrently in a single wave:
+//   k_decide        one warp per walker: the Metropolis decision with the reference's exact predicate and
+//                   RNG consumption order, the integer state changes (kappa, Z_mu, counters) and an
+//                   "accepted" record (walker, K_up, l_up, K_dn, l_dn, pending count);
+//   k_build_factors one CTA per accepted (walker, species): appends the factor pair of the move.
 template <bool REPLAY>
-__global__ void __launch_bounds__(128)
-k_propose_delayed(DevState S, int gate_refresh, const double *__restrict__ rp_r,
-                  const int *__restrict__ rp_bond, const int *__restrict__ rp_pick) {
-    constexpr int NT = 128;
-    __shared__ int sh_i[8];                                    // accepted, K_up, l_up, K_dn, l_dn
-    __shared__ double s_bl[2][32], s_ak[2][32];
-    const int w = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31;
+__global__ void __launch_bounds__(256, 4)
+k_decide(DevState S, int parity, int gate_refresh, const double *__restrict__ rp_r,
+         const int *__restrict__ rp_bond, const int *__restrict__ rp_pick) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= S.nw) return;
     const int ns = S.ns;
+    int *kup = S.kup + (size_t)w * ns;
+    int *kdn = S.kdn + (size_t)w * ns;
     const int cnt = S.fcnt[w];
-    if (tid < 32) {
-        int *kup = S.kup + (size_t)w * ns;
-        int *kdn = S.kdn + (size_t)w * ns;
-        const int zmu = S.zmu[w];
-        Xoshiro g;
-        if (!REPLAY) {
-            const unsigned long long *st = S.rng + (size_t)w * 4;
-            g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
+    const int zmu = S.zmu[w];
+    Xoshiro g;
+    if (!REPLAY) {
+        const unsigned long long *st = S.rng + (size_t)w * 4;
+        g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
+    }
+    const double r = REPLAY ? rp_r[w] : g.rand_f64();               // :546
+    const double zr = (double)zmu / (double)S.n_bonds;
+    bool accepted = false, reached = false;
+    int i = 0, site = 0, flag = 0, l_up = 0, l_dn = 0, K_up = 0, K_dn = 0;
+    int ku_i = 0, ku_s = 0, kd_i = 0, kd_s = 0;
+    if (!(r > zr)) {                                                // :547-550
+        long long b = REPLAY ? (long long)rp_bond[w] : g.rand_index((unsigned long long)S.n_bonds);  // :552
+        if (b < 1) b = 1;
+        if (b > S.n_bonds) b = S.n_bonds;
+        i = S.bi[b - 1];
+        site = S.bj[b - 1];
+        ku_i = kup[i]; ku_s = kup[site]; kd_i = kdn[i]; kd_s = kdn[site];
+        const bool f1 = ku_i != 0 && kd_s != 0;                     // :558-561
+        const bool f2 = ku_s != 0 && kd_i != 0;
+        if (f1 || f2) {
+            const int nm = (int)f1 + (int)f2;
+            long long pick;                                         // :569
+            if (REPLAY) pick = rp_pick ? (long long)rp_pick[w] : 1;
+            else pick = g.rand_index((unsigned long long)nm);
+            flag = (f1 && f2) ? (pick == 1 ? 1 : 2) : (f1 ? 1 : 2);
+            l_up = flag == 1 ? ku_i : ku_s;                         // :572-573
+            l_dn = flag == 1 ? kd_s : kd_i;
+            K_up = flag == 1 ? site : i;
+            K_dn = flag == 1 ? i : site;
+            const double wu = w_entry_warp(S, w, 0, K_up, l_up - 1, cnt, lane);   // :576-580
+            const double wd = w_entry_warp(S, w, 1, K_dn, l_dn - 1, cnt, lane);
+            const double ratio = wu * wd;
+            const double p = ratio * ratio;                         // abs2(ratio)
+            if (p >= 1.0 && r < zr) accepted = true;                // :582-587
+            else if (p < 1.0 && r < zr * p) accepted = true;
+            if (!(p == p) || p > 1.79e308) {
+                if (lane == 0) atomicOr(&S.flags[w], KDSL_FLAG_NONFINITE_DEV);
+            }
+            reached = true;
         }
-        const double r = REPLAY ? rp_r[w] : g.rand_f64();           // :546
-        const double zr = (double)zmu / (double)S.n_bonds;
-        bool accepted = false, reached = false;
-        int i = 0, site = 0, flag = 0, l_up = 0, l_dn = 0, K_up = 0, K_dn = 0;
-        int ku_i = 0, ku_s = 0, kd_i = 0, kd_s = 0;
-        if (!(r > zr)) {                                            // :547-550
-            long long b = REPLAY ? (long long)rp_bond[w] : g.rand_index((unsigned long long)S.n_bonds);  // :552
-            if (b < 1) b = 1;
-            if (b > S.n_bonds) b = S.n_bonds;
-            i = S.bi[b - 1];
-            site = S.bj[b - 1];
-            ku_i = kup[i]; ku_s = kup[site]; kd_i = kdn[i]; kd_s = kdn[site];
-            const bool f1 = ku_i != 0 && kd_s != 0;                 // :558-561
-            const bool f2 = ku_s != 0 && kd_i != 0;
-            if (f1 || f2) {
-                const int nm = (int)f1 + (int)f2;
-                long long pick;                                     // :569
-                if (REPLAY) pick = rp_pick ? (long long)rp_pick[w] : 1;
-                else pick = g.rand_index((unsigned long long)nm);
-                flag = (f1 && f2) ? (pick == 1 ? 1 : 2) : (f1 ? 1 : 2);
-                l_up = flag == 1 ? ku_i : ku_s;                     // :572-573
-                l_dn = flag == 1 ? kd_s : kd_i;
-                K_up = flag == 1 ? site : i;
-                K_dn = flag == 1 ? i : site;
-                const double wu = w_entry_warp(S, w, 0, K_up, l_up - 1, cnt, lane);   // :576-580
-                const double wd = w_entry_warp(S, w, 1, K_dn, l_dn - 1, cnt, lane);
-                const double ratio = wu * wd;
-                const double p = ratio * ratio;                     // abs2(ratio)
-                if (p >= 1.0 && r < zr) accepted = true;            // :582-587
-                else if (p < 1.0 && r < zr * p) accepted = true;
-                if (!(p == p) || p > 1.79e308) {
-                    if (lane == 0) atomicOr(&S.flags[w], KDSL_FLAG_NONFINITE_DEV);
-                }
-                reached = true;
-            }
+    }
+    if (accepted) {
+        const int ui_o = ku_i != 0, di_o = kd_i != 0, us_o = ku_s != 0, ds_o = kd_s != 0;
+        const int ui_n = flag == 1 ? 0 : 1, di_n = flag == 1 ? 1 : 0;
+        const int us_n = flag == 1 ? 1 : 0, ds_n = flag == 1 ? 0 : 1;
+        int delta = 0;
+        for (int q = S.adj_off[i] + lane; q < S.adj_off[i + 1]; q += 32) {
+            const int n = S.adj_nbr[q];
+            if (n == site) continue;
+            const int un = kup[n] != 0, dn = kdn[n] != 0;
+            delta += bond_is_anti(ui_n, di_n, un, dn) - bond_is_anti(ui_o, di_o, un, dn);
         }
-        if (accepted) {
-            const int ui_o = ku_i != 0, di_o = kd_i != 0, us_o = ku_s != 0, ds_o = kd_s != 0;
-            const int ui_n = flag == 1 ? 0 : 1, di_n = flag == 1 ? 1 : 0;
-            const int us_n = flag == 1 ? 1 : 0, ds_n = flag == 1 ? 0 : 1;
-            int delta = 0;
-            for (int q = S.adj_off[i] + lane; q < S.adj_off[i + 1]; q += 32) {
-                const int n = S.adj_nbr[q];
-                if (n == site) continue;
-                const int un = kup[n] != 0, dn = kdn[n] != 0;
-                delta += bond_is_anti(ui_n, di_n, un, dn) - bond_is_anti(ui_o, di_o, un, dn);
-            }
-            for (int q = S.adj_off[site] + lane; q < S.adj_off[site + 1]; q += 32) {
-                const int n = S.adj_nbr[q];
-                if (n == i) continue;
-                const int un = kup[n] != 0, dn = kdn[n] != 0;
-                delta += bond_is_anti(us_n, ds_n, un, dn) - bond_is_anti(us_o, ds_o, un, dn);
-            }
-            if (lane == 0)
-                delta += bond_is_anti(ui_n, di_n, us_n, ds_n) - bond_is_anti(ui_o, di_o, us_o, ds_o);
-            delta = warp_sum_int(delta);
-            if (lane == 0) {
-                S.zmu[w] = zmu + delta;
-                if (flag == 1) {                                    // :502-503
-                    kup[i] = 0; kup[site] = l_up;
-                    kdn[i] = l_dn; kdn[site] = 0;
-                } else {                                            // :508-509
-                    kup[i] = l_up; kup[site] = 0;
-                    kdn[i] = 0; kdn[site] = l_dn;
-                }
-                S.n_acc[w] += 1ull;
-            }
+        for (int q = S.adj_off[site] + lane; q < S.adj_off[site + 1]; q += 32) {
+            const int n = S.adj_nbr[q];
+            if (n == i) continue;
+            const int un = kup[n] != 0, dn = kdn[n] != 0;
+            delta += bond_is_anti(us_n, ds_n, un, dn) - bond_is_anti(us_o, ds_o, un, dn);
         }
+        if (lane == 0)
+            delta += bond_is_anti(ui_n, di_n, us_n, ds_n) - bond_is_anti(ui_o, di_o, us_o, ds_o);
+        delta = warp_sum_int(delta);
         if (lane == 0) {
-            sh_i[0] = (accepted && !gate_refresh) ? 1 : 0;
-            sh_i[1] = K_up; sh_i[2] = l_up - 1; sh_i[3] = K_dn; sh_i[4] = l_dn - 1;
-            if (reached) {
-                S.n_reach[w] += 1ull;
-                if (gate_refresh) {                                 // :595
-                    const int slot = atomicAdd(&S.cnt[2], 1);
-                    S.ref_list[slot] = w;
+            S.zmu[w] = zmu + delta;
+            if (flag == 1) {                                        // :502-503
+                kup[i] = 0; kup[site] = l_up;
+                kdn[i] = l_dn; kdn[site] = 0;
+            } else {                                                // :508-509
+                kup[i] = l_up; kup[site] = 0;
+                kdn[i] = 0; kdn[site] = l_dn;
+            }
+            S.n_acc[w] += 1ull;
+            if (!gate_refresh) {                                    // (a walker re-evaluated this sweep needs no factor)
+                const int slot = atomicAdd(&S.cnt[parity], 1);
+                int *rec = S.acc_list + ((size_t)parity * S.nw + slot) * 6;
+                rec[0] = w; rec[1] = K_up; rec[2] = l_up - 1; rec[3] = K_dn; rec[4] = l_dn - 1; rec[5] = cnt;
+                S.fcnt[w] = cnt + 1;
+                if (cnt + 1 == S.kth) {                             // due for a flush (listed exactly once)
+                    const int fs = atomicAdd(&S.cnt[4], 1);
+                    S.flush_list[fs] = w;
                 }
             }
-            if (!REPLAY) {
-                unsigned long long *st = S.rng + (size_t)w * 4;
-                st[0] = g.s0; st[1] = g.s1; st[2] = g.s2; st[3] = g.s3;
+        }
+    }
+    if (lane == 0) {
+        if (reached) {
+            S.n_reach[w] += 1ull;
+            if (gate_refresh) {                                     // :595
+                const int slot = atomicAdd(&S.cnt[2], 1);
+                S.ref_list[slot] = w;
             }
         }
-    }
-    __syncthreads();
-    if (!sh_i[0]) return;
-    // accepted (and not about to be re-evaluated from scratch): append the factor pair of this move
-    const int K_up = sh_i[1], l_up = sh_i[2], K_dn = sh_i[3], l_dn = sh_i[4];
-    if (tid < cnt) {
-        s_bl[0][tid] = S.facB_up[((size_t)w * S.kmax + tid) * S.n_up + l_up];
-        s_ak[0][tid] = S.facA_up[((size_t)w * S.kmax + tid) * ns + K_up];
-    } else if (tid >= 32 && tid - 32 < cnt) {
-        const int m = tid - 32;
-        s_bl[1][m] = S.facB_dn[((size_t)w * S.kmax + m) * S.n_dn + l_dn];
-        s_ak[1][m] = S.facA_dn[((size_t)w * S.kmax + m) * ns + K_dn];
-    }
-    __syncthreads();
-    build_factor_cta<NT>(S, w, 0, K_up, l_up, cnt, s_bl[0], s_ak[0], tid);
-    build_factor_cta<NT>(S, w, 1, K_dn, l_dn, cnt, s_bl[1], s_ak[1], tid);
-    if (tid == 0) {
-        S.fcnt[w] = cnt + 1;
-        if (cnt + 1 == S.kth) {                                     // due for a flush (listed exactly once)
-            const int slot = atomicAdd(&S.cnt[4], 1);
-            S.flush_list[slot] = w;
+        if (!REPLAY) {
+            unsigned long long *st = S.rng + (size_t)w * 4;
+            st[0] = g.s0; st[1] = g.s1; st[2] = g.s2; st[3] = g.s3;
         }
+    }
+}
+
+// grid-stride over (accepted record, species); 256 threads per item
+template <int KMX>
+__global__ void __launch_bounds__(256)
+k_build_factors(DevState S, int parity) {
+    constexpr int NT = 256;
+    __shared__ double s_bl[32], s_ak[32];
+    const int n_items = 2 * S.cnt[parity];
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) S.cnt[parity ^ 1] = 0;      // arm the other list for the next sweep
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int *rec = S.acc_list + ((size_t)parity * S.nw + (item >> 1)) * 6;
+        const int spin = item & 1;
+        const int w = rec[0], K = rec[1 + 2 * spin], l = rec[2 + 2 * spin], cnt = rec[5];
+        const int N = spin ? S.n_dn : S.n_up;
+        __syncthreads();
+        if (tid < cnt) {
+            s_bl[tid] = (spin ? S.facB_dn : S.facB_up)[((size_t)w * S.kmax + tid) * N + l];
+            s_ak[tid] = (spin ? S.facA_dn : S.facA_up)[((size_t)w * S.kmax + tid) * S.ns + K];
+        }
+        __syncthreads();
+        build_factor_cta<NT, KMX>(S, w, spin, K, l, cnt, s_bl, s_ak, tid);
     }
 }
 

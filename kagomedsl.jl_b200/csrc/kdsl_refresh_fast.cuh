@@ -55,11 +55,22 @@ k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restri
     }
 }
 
-template <int NB, int RPT>
-__global__ void __launch_bounds__(256, (RPT == 1 ? 2 : 1))
+// developer instrumentation: SM cycles spent by CTA 0 in each phase of k_inverse_blocked
+__device__ long long g_inv_phase_cycles[8];
+#define PHASE_TICK(idx)                                                  \
+    do {                                                                 \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                       \
+            const long long now_ = clock64();                            \
+            g_inv_phase_cycles[idx] += now_ - t_phase;                   \
+            t_phase = now_;                                              \
+        }                                                                \
+    } while (0)
+
+template <int NB, int RPT, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
                   int *__restrict__ status, int *__restrict__ colsrc_base, int Np, int cs_stride) {
-    constexpr int T = 256;
+    constexpr int NWARP = T / 32;
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (b >= batch_count(S, list)) return;
@@ -67,9 +78,9 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
     double *sU = sL + (size_t)Np * NB;                 // [Np x NB] frag-major, holds U_K,:
     double *sLU = sU + (size_t)Np * NB;                // [NB x NB] row-major packed LU of the pivot block
     double *sRow = sLU + NB * NB;                      // [2][NB] row exchange
-    double *sRed = sRow + 2 * NB;                      // [8] warp maxima
-    int *sRedI = reinterpret_cast<int *>(sRed + 8);    // [8] their rows
-    int *sPiv = sRedI + 8;                             // [Np] pivot row chosen at each elimination step
+    double *sRed = sRow + 2 * NB;                      // [NWARP] warp maxima
+    int *sRedI = reinterpret_cast<int *>(sRed + NWARP);  // [NWARP] their rows
+    int *sPiv = sRedI + NWARP;                         // [Np] pivot row chosen at each elimination step
     int *sMvPos = sPiv + Np;                           // [2*NB] displaced-row moves of the current panel
     int *sMvSrc = sMvPos + 2 * NB;                     // [2*NB]
     int *sSrcK = sMvSrc + 2 * NB;                      // [NB] source row of each pivot position
@@ -79,6 +90,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < NB * NB; e += T) sLU[e] = 0.0;
     __syncthreads();
+    long long t_phase = clock64();
 
     for (int k0 = 0; k0 < Np; k0 += NB) {
         const int kw = min(NB, Np - k0);               // multiple of 8
@@ -90,6 +102,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
 #pragma unroll
             for (int k = 0; k < NB; k++) a[r][k] = (i < Np && k < kw) ? A[(size_t)(k0 + k) * Np + i] : 0.0;
         }
+        PHASE_TICK(0);
         // ---- 2. LU of the panel with partial pivoting over the not-yet-pivoted rows (>= k0+k);
         //         rows above k0 are eliminated as well (Gauss-Jordan) ----
 #pragma unroll
@@ -118,7 +131,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                 double bv = sRed[0];
                 int p = sRedI[0];
 #pragma unroll
-                for (int q = 1; q < 8; q++) {
+                for (int q = 1; q < NWARP; q++) {
                     const double ov = sRed[q];
                     const int oi = sRedI[q];
                     if (ov > bv || (ov == bv && oi < p)) { bv = ov; p = oi; }
@@ -169,6 +182,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                 __syncthreads();
             }
         }
+        PHASE_TICK(1);
         // ---- 3. publish -L' (zero on the pivot rows) and the packed LU of the pivot block ----
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
@@ -180,25 +194,35 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                 if (is_piv) {
 #pragma unroll
                     for (int k = 0; k < NB; k++) sLU[(i - k0) * NB + k] = a[r][k];
+#pragma unroll
+                    for (int k = 0; k < NB; k++) if (k == i - k0) sRow[k] = 1.0 / a[r][k];   // 1 / U_kk
                 }
             }
         }
-        // composed row interchanges of this panel: which original row lands on each touched position
+        // composed row interchanges of this panel: which original row lands on each touched position.
+        // sIdx (scratch in the not-yet-written sU region) maps a row to its slot in the move list.
+        int *sIdx = reinterpret_cast<int *>(sU);
+        for (int k = tid; k < kw; k += T) sIdx[sPiv[k0 + k]] = -1;
+        __syncthreads();
         if (tid == 0) {
             int n = 0;
             for (int k = 0; k < kw; k++) { sMvPos[n] = k0 + k; sMvSrc[n] = k0 + k; n++; }
             for (int k = 0; k < kw; k++) {
                 const int p = sPiv[k0 + k];
                 if (p == k0 + k) continue;
-                int ip = -1;
-                for (int q = 0; q < n; q++) if (sMvPos[q] == p) ip = q;
-                if (ip < 0) { sMvPos[n] = p; sMvSrc[n] = p; ip = n; n++; }
+                int ip;
+                if (p < k0 + kw) ip = p - k0;                      // another pivot position
+                else {
+                    ip = sIdx[p];
+                    if (ip < 0) { sMvPos[n] = p; sMvSrc[n] = p; sIdx[p] = n; ip = n; n++; }
+                }
                 const int t0 = sMvSrc[k]; sMvSrc[k] = sMvSrc[ip]; sMvSrc[ip] = t0;
             }
             for (int k = 0; k < kw; k++) sSrcK[k] = sMvSrc[k];
             sNmv = n;                                              // entries [kw, n) are displaced rows outside the pivot block
         }
         __syncthreads();
+        PHASE_TICK(2);
         // ---- 4. per column outside the panel: apply the interchanges, U_K,j = L_KK^-1 A_K,j (kept for
         //         the update), final pivot rows A_K,j = U_KK^-1 U_K,j ----
         const int nmv = sNmv;
@@ -231,13 +255,14 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                     if (k < kw) {
 #pragma unroll
                         for (int m = k + 1; m < NB; m++) u[k] = fma(-sLU[k * NB + m], u[m], u[k]);
-                        u[k] = u[k] / sLU[k * NB + k];
+                        u[k] = u[k] * sRow[k];
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < NB; k++) if (k < kw) col[k0 + k] = u[k];
             }
         }
+        PHASE_TICK(3);
         // ---- 5. the panel columns of the result: A_IK = -L' L_KK^-1 (other rows), A_KK = U_KK^-1 L_KK^-1 ----
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
@@ -251,7 +276,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                         double y = (k == q) ? 1.0 : 0.0;
 #pragma unroll
                         for (int m = 0; m < k; m++) y = fma(-x[m], sLU[m * NB + k], y);
-                        x[k] = (k < kw && k >= q) ? y / sLU[k * NB + k] : 0.0;
+                        x[k] = (k < kw && k >= q) ? y * sRow[k] : 0.0;
                     }
                 } else {
 #pragma unroll
@@ -269,13 +294,14 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
             }
         }
         __syncthreads();
+        PHASE_TICK(4);
         // ---- 6. rank-kw update of everything outside the pivot rows / panel columns on the FP64
         //         tensor pipe: A_I,J += (-L'_I) U_K,J.  Work item = 32-row strip x group of 4 col tiles ----
         {
             const int strips = (Np + 31) >> 5, ctiles = Np >> 3;
             const int cgroups = (ctiles + 3) >> 2;
             const int gr = lane >> 2, tg = lane & 3;
-            for (int item = warp; item < strips * cgroups; item += 8) {
+            for (int item = warp; item < strips * cgroups; item += NWARP) {
                 const int strip = item / cgroups, cg = item - strip * cgroups;
                 const int r0 = strip << 5;
                 double af[4][NB / 4];
@@ -288,26 +314,24 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                     for (int s = 0; s < NB / 4; s++)
                         af[m][s] = mval[m] ? sL[((((rt >> 3) * (NB >> 2)) + s) << 5) + lane] : 0.0;
                 }
-                for (int ct = cg * 4; ct < min(cg * 4 + 4, ctiles); ct++) {
-                    const int c0 = ct << 3;
-                    if (c0 >= k0 && c0 < k0 + kw) continue;
-                    double c[4][2];
-                    double *p0 = A + (size_t)(c0 + 2 * tg) * Np + r0 + gr;
+                const int ct_end = min(cg * 4 + 4, ctiles);
+                auto tile_ok = [&](int ct) { return ct < ct_end && !((ct << 3) >= k0 && (ct << 3) < k0 + kw); };
+                auto load_c = [&](int ct, double (&c)[4][2]) {
+                    const double *p0 = A + (size_t)((ct << 3) + 2 * tg) * Np + r0 + gr;
 #pragma unroll
                     for (int m = 0; m < 4; m++) {
-                        if (mval[m]) {
-                            c[m][0] = p0[8 * m];
-                            c[m][1] = p0[8 * m + Np];
-                        } else {
-                            c[m][0] = 0.0; c[m][1] = 0.0;
-                        }
+                        c[m][0] = mval[m] ? p0[8 * m] : 0.0;
+                        c[m][1] = mval[m] ? p0[8 * m + Np] : 0.0;
                     }
+                };
+                auto mma_store = [&](int ct, double (&c)[4][2]) {
 #pragma unroll
                     for (int s = 0; s < NB / 4; s++) {
                         const double bf = sU[(((ct * (NB >> 2)) + s) << 5) + lane];
 #pragma unroll
                         for (int m = 0; m < 4; m++) dmma_8x8x4(c[m][0], c[m][1], af[m][s], bf);
                     }
+                    double *p0 = A + (size_t)((ct << 3) + 2 * tg) * Np + r0 + gr;
 #pragma unroll
                     for (int m = 0; m < 4; m++) {
                         if (mval[m]) {
@@ -315,10 +339,22 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
                             p0[8 * m + Np] = c[m][1];
                         }
                     }
-                }
+                };
+                // the (up to) 4 column tiles of this item, two tiles of loads in flight ahead of the DMMAs
+                double c0[4][2], c1[4][2];
+                const int ctb = cg * 4;
+                if (tile_ok(ctb)) load_c(ctb, c0);
+                if (tile_ok(ctb + 1)) load_c(ctb + 1, c1);
+                if (tile_ok(ctb)) mma_store(ctb, c0);
+                if (tile_ok(ctb + 2)) load_c(ctb + 2, c0);
+                if (tile_ok(ctb + 1)) mma_store(ctb + 1, c1);
+                if (tile_ok(ctb + 3)) load_c(ctb + 3, c1);
+                if (tile_ok(ctb + 2)) mma_store(ctb + 2, c0);
+                if (tile_ok(ctb + 3)) mma_store(ctb + 3, c1);
             }
         }
         __syncthreads();
+        PHASE_TICK(5);
     }
     // ---- 7. inv(A) = R * P: record which stored column of R is each column of the inverse ----
     int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
@@ -338,7 +374,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
 // W[w] (ns x N) = U (ns x N) * X,  X[:, j] = R[:, colsrc[j]] (R stored with leading dimension Np).
 // grid (tiles_m * tiles_n, nw, 2), 288 threads = 9 warps in a 3x3 arrangement of 24x24 warp tiles.
 template <int KT>
-__global__ void __launch_bounds__(288)
+__global__ void __launch_bounds__(288, 2)
 k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict__ X_up,
               const double *__restrict__ X_dn, const int *__restrict__ status,
               const int *__restrict__ colsrc_base, int Np_up, int Np_dn, int cs_stride) {

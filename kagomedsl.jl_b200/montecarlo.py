@@ -287,6 +287,11 @@ class Engine:
     def synchronize(self):
         check(self._L.kdsl_synchronize(self._h))
 
+    def fp64_dmma_peak_tflops(self) -> float:
+        v = C.c_double(0.0)
+        check(self._L.kdsl_bench_fp64_dmma(self._h, C.byref(v)))
+        return v.value
+
     def event_record(self, slot: int):
         check(self._L.kdsl_event_record(self._h, int(slot)))
 
