@@ -293,7 +293,7 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
                     k_decide<false><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, nullptr, nullptr, nullptr);
                 CK(cudaGetLastError());
                 if (!gate) {                    // (at a gate sweep nobody is listed: accepted walkers are re-evaluated)
-                    k_build_factors<KDSL_KMAX><<<h->num_sms * 8, 256, 0, h->stream>>>(S, h->parity);
+                    k_build_factors<KDSL_KMAX><<<h->num_sms * 8, 128, 0, h->stream>>>(S, h->parity);
                     h->parity ^= 1;
                 }
             } else if (replay) {

@@ -190,11 +190,12 @@ k_decide(DevState S, int parity, int gate_refresh, const double *__restrict__ rp
     }
 }
 
-// grid-stride over (accepted record, species); 256 threads per item
+// grid-stride over (accepted record, species); 128 threads per item, 8 CTAs per SM so that all
+// (~2 x 0.13 x n_walkers) items of a sweep are resident in one wave
 template <int KMX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 8)
 k_build_factors(DevState S, int parity) {
-    constexpr int NT = 256;
+    constexpr int NT = 128;
     __shared__ double s_bl[32], s_ak[32];
     const int n_items = 2 * S.cnt[parity];
     const int tid = threadIdx.x;

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=432)
     ap.add_argument("--therm", type=int, default=432)
     ap.add_argument("--opt", action="append", default=[], help="name=value engine options")
+    ap.add_argument("--no-prof", action="store_true")
     args = ap.parse_args()
     lat = kd.DoubleKagome(1.0, args.n, args.n, (True, True), (True, False))
     ns = kd.ns(lat)
@@ -38,7 +39,7 @@ def main():
     eng.synchronize()
     eng.reset_accumulators()
     eng.reset_timers()
-    eng.set_profiling(True)
+    eng.set_profiling(not args.no_prof)
     t0 = time.time()
     eng.sweep(args.sweeps, 0)
     eng.synchronize()
@@ -54,6 +55,7 @@ def main():
         "timers": tm,
         "update_GBs": upd["moves"] * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
         "flush_GBs": upd["flushes"] * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
+        "launches_total": sum(v["launches"] for v in tm.values()),
     }, indent=1))
     # pure W-update bandwidth: every walker gets one move
     eng.set_profiling(True)
