@@ -17,6 +17,7 @@
 #include "kdsl_refresh.cuh"
 #include "kdsl_refresh_fast.cuh"
 #include "kdsl_delayed.cuh"
+#include "kdsl_woodbury.cuh"
 #include "kdsl_update.cuh"
 
 #define KDSL_VERSION_NUM 110
@@ -74,7 +75,7 @@ struct kdsl_handle_s {
     int64_t walker_sweeps = 0;
     // options
     int64_t refresh_every = 0;
-    int update_variant = 1, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
+    int update_variant = 2, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
     int since_flush = 0;
     int inverse_tuning = 0;
     int update_ch = 8;
@@ -155,6 +156,10 @@ struct Span {
 };
 
 int grid_for_warps(int nw) { return (nw * 32 + 255) / 256; }
+
+size_t measure_wb_smem(const DevState &S) {
+    return ((size_t)S.kmax * (S.n_up + S.n_dn) + 2 * (size_t)S.kmax * S.kmax) * sizeof(double) + 4 * S.kmax * sizeof(int);
+}
 
 int launch_update(kdsl_handle h, int parity) {
     const DevState &S = h->S;
@@ -247,14 +252,24 @@ int launch_flush(kdsl_handle h, bool all) {
     const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KDSL_KMAX * sizeof(double);
     static bool attr = false;
     if (!attr) {
-        CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_measure_wb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
     {
         Span sp(h, KDSL_T_UPDATE);
-        k_flush<KDSL_KMAX><<<h->num_sms * 4, 288, smem, h->stream>>>(S, all ? nullptr : S.flush_list, all ? nullptr : S.cnt + 4, S.nw);
+        const int *list = all ? nullptr : S.flush_list;
+        int *cptr = all ? nullptr : S.cnt + 4;
+        if (h->update_variant == 2) {
+            const size_t psm = (size_t)S.kmax * S.kmax * sizeof(double) + 2 * S.kmax * sizeof(int);
+            k_flush_prepare<<<h->num_sms * 4, 256, psm, h->stream>>>(S, list, cptr, S.nw);
+            CK(cudaGetLastError());
+        }
+        if (h->update_variant == 2) k_flush<KDSL_KMAX, true><<<h->num_sms * 4, 288, smem, h->stream>>>(S, list, cptr, S.nw);
+        else k_flush<KDSL_KMAX, false><<<h->num_sms * 4, 288, smem, h->stream>>>(S, list, cptr, S.nw);
         CK(cudaGetLastError());
-        k_flush_done<<<8, 256, 0, h->stream>>>(S, all ? nullptr : S.flush_list, all ? nullptr : S.cnt + 4, S.nw);
+        k_flush_done<<<8, 256, 0, h->stream>>>(S, list, cptr, S.nw);
         CK(cudaGetLastError());
         k_zero_int<<<1, 1, 0, h->stream>>>(S.cnt + 4);
         CK(cudaGetLastError());
@@ -281,11 +296,19 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
     const int pgrid = grid_for_warps(S.nw);
     for (int64_t s = 0; s < n; s++) {
         const bool gate = (h->sweeps % period) == 0;            // src/MonteCarlo.jl:595 (pre-increment)
-        const bool delayed = h->update_variant == 1;
+        const bool delayed = h->update_variant >= 1;
+        const bool woodbury = h->update_variant == 2;
         {
             Span sp(h, KDSL_T_PROPOSE);
             const size_t off = (size_t)s * S.nw;
-            if (delayed) {
+            if (woodbury) {
+                if (replay)
+                    k_decide_wb<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
+                                                                    have_pick ? h->rp_pick + off : nullptr);
+                else
+                    k_decide_wb<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, nullptr, nullptr, nullptr);
+                CK(cudaGetLastError());
+            } else if (delayed) {
                 if (replay)
                     k_decide<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
                                                                  have_pick ? h->rp_pick + off : nullptr);
@@ -321,7 +344,8 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
         h->walker_sweeps += S.nw;
         if (therm >= 0 && h->sweeps > therm && (h->sweeps % S.n_occ) == 0) {   // :630 (post-increment)
             Span sp(h, KDSL_T_MEASURE);
-            if (delayed) k_measure_delayed<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
+            if (woodbury) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, nullptr, 1);
+            else if (delayed) k_measure_delayed<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             else k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             CK(cudaGetLastError());
         }
@@ -483,7 +507,8 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;
     ALLOC(S.facA_up, nw * S.kmax * ns); ALLOC(S.facA_dn, nw * S.kmax * ns);
     ALLOC(S.facB_up, nw * S.kmax * n_up); ALLOC(S.facB_dn, nw * S.kmax * n_dn);
-    ALLOC(S.fcnt, nw); ALLOC(S.flush_list, nw);
+    ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw);
+    ALLOC(S.wbT, 2 * nw * S.kmax * S.kmax); ALLOC(S.wbK, 2 * nw * S.kmax); ALLOC(S.wbL, 2 * nw * S.kmax);
     h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
     ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
@@ -567,7 +592,7 @@ int kdsl_set_config(kdsl_handle h, const int32_t *kup, const int32_t *kdn) {
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(S.cnt, 0, 8 * sizeof(int), h->stream));
     CK(cudaMemsetAsync(S.flags, 0, (size_t)S.nw * sizeof(int), h->stream));
-    CK(cudaMemsetAsync(S.fcnt, 0, (size_t)S.nw * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(S.fcnt, 0, (size_t)2 * S.nw * sizeof(int), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->parity = 0;
     h->since_flush = 0;
@@ -669,7 +694,8 @@ int kdsl_measure(kdsl_handle h, double *ol) {
     const DevState &S = h->S;
     {
         Span sp(h, KDSL_T_MEASURE);
-        k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+        if (h->update_variant == 2) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, h->d_tmp_d, 0);
+        else k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(ol, h->d_tmp_d, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -744,7 +770,7 @@ int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     if (!out || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / out");
     const int N = spin ? S.n_dn : S.n_up;
     const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
-    if (h->update_variant == 1 && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
+    if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double), cudaMemcpyDeviceToHost));
     return KDSL_OK;
@@ -757,7 +783,7 @@ int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
     if (!in || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / in");
     const int N = spin ? S.n_dn : S.n_up;
     double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
-    if (h->update_variant == 1 && (rc = launch_flush(h, true))) return rc;
+    if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double), cudaMemcpyHostToDevice));
     return KDSL_OK;
@@ -781,7 +807,7 @@ int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32
         mv[m] = walker[m]; mv[n_moves + m] = l_up[m]; mv[2 * (size_t)n_moves + m] = K_up[m];
         mv[3 * (size_t)n_moves + m] = l_dn[m]; mv[4 * (size_t)n_moves + m] = K_dn[m];
     }
-    if (h->update_variant == 1 && (rc = launch_flush(h, true))) return rc;
+    if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;
     int *d_mv = nullptr;
     CK(cudaMalloc(&d_mv, mv.size() * sizeof(int)));
     CK(cudaMemcpyAsync(d_mv, mv.data(), mv.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -863,7 +889,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         if (value < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "refresh_every must be >= 0");
         h->refresh_every = value;
     } else if (n == "update_variant") {
-        if (value != 0 && value != 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming) or 1 (delayed rank-k)");
+        if (value < 0 || value > 2) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming), 1 (delayed factor lists) or 2 (delayed, Woodbury form)");
         if (h->have_config && h->W_valid) {
             int rc = use_device(h);
             if (rc) return rc;

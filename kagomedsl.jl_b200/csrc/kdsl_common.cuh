@@ -37,7 +37,9 @@ struct DevState {
     // delayed (rank-k) updates: W = W0 + sum_{m<fcnt} A_m (x) B_m
     double *facA_up, *facA_dn;   // [nw][kmax][ns]
     double *facB_up, *facB_dn;   // [nw][kmax][N]
-    int *fcnt;                   // [nw] pending factors per walker
+    int *fcnt;                   // [nw][2] pending update count per walker and species
+    double *wbT;                 // [nw][2][kmax*kmax] Woodbury state: T = inv(W0[K_set, L])
+    int *wbK, *wbL;              // [nw][2][kmax] displaced particles: label wbL now sits on site wbK
     int *flush_list;             // [nw] walkers that reached kth pending factors (count in cnt[4])
     int kmax, kth;
 };

@@ -90,7 +90,7 @@ k_decide(DevState S, int parity, int gate_refresh, const double *__restrict__ rp
     const int ns = S.ns;
     int *kup = S.kup + (size_t)w * ns;
     int *kdn = S.kdn + (size_t)w * ns;
-    const int cnt = S.fcnt[w];
+    const int cnt = S.fcnt[2 * w];
     const int zmu = S.zmu[w];
     Xoshiro g;
     if (!REPLAY) {
@@ -167,7 +167,8 @@ k_decide(DevState S, int parity, int gate_refresh, const double *__restrict__ rp
                 const int slot = atomicAdd(&S.cnt[parity], 1);
                 int *rec = S.acc_list + ((size_t)parity * S.nw + slot) * 6;
                 rec[0] = w; rec[1] = K_up; rec[2] = l_up - 1; rec[3] = K_dn; rec[4] = l_dn - 1; rec[5] = cnt;
-                S.fcnt[w] = cnt + 1;
+                S.fcnt[2 * w] = cnt + 1;
+                S.fcnt[2 * w + 1] = cnt + 1;
                 if (cnt + 1 == S.kth) {                             // due for a flush (listed exactly once)
                     const int fs = atomicAdd(&S.cnt[4], 1);
                     S.flush_list[fs] = w;
@@ -218,7 +219,9 @@ k_build_factors(DevState S, int parity) {
 // W0 += sum_m A_m (x) B_m for the listed walkers: the HBM-bound pass of the delayed update.
 // Work item = (list entry, species, block of 216 rows); 288 threads = 9 warps, each warp owns a strip
 // of 24 rows (3 DMMA m-tiles) and walks over all column tiles.  KPAD = padded factor count.
-template <int KPAD>
+// FROM_W0: the left operand A_m is column l_m (wbL) of W0 itself (Woodbury form) instead of facA[m]; a warp loads
+// its rows of those columns into registers before it overwrites them, and no other warp touches these rows.
+template <int KPAD, bool FROM_W0>
 __global__ void __launch_bounds__(288)
 k_flush(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed) {
     extern __shared__ double fsm[];                      // B operand, frag-major [Ncols8 x KPAD]
@@ -233,7 +236,7 @@ k_flush(DevState S, const int *__restrict__ list, const int *__restrict__ count_
         const int rem = (int)(item - (long long)e * 2 * nrb);
         const int spin = rem / nrb, rb = rem - spin * nrb;
         const int w = list ? list[e] : e;
-        const int cnt = S.fcnt[w];
+        const int cnt = S.fcnt[2 * w + spin];
         if (cnt == 0) continue;                           // uniform over the block
         const int N = spin ? S.n_dn : S.n_up;
         const double *A = (spin ? S.facA_dn : S.facA_up) + (size_t)w * S.kmax * ns;
@@ -253,7 +256,10 @@ k_flush(DevState S, const int *__restrict__ list, const int *__restrict__ count_
 #pragma unroll
             for (int s = 0; s < KPAD / 4; s++) {
                 const int m = 4 * s + tg;
-                af[t][s] = (row < ns && m < cnt) ? A[(size_t)m * ns + row] : 0.0;
+                if (FROM_W0)
+                    af[t][s] = (row < ns && m < cnt) ? W0[(size_t)S.wbL[((size_t)w * 2 + spin) * S.kmax + m] * ns + row] : 0.0;
+                else
+                    af[t][s] = (row < ns && m < cnt) ? A[(size_t)m * ns + row] : 0.0;
             }
         }
         __syncthreads();
@@ -299,8 +305,11 @@ k_flush(DevState S, const int *__restrict__ list, const int *__restrict__ count_
 // after k_flush: the listed walkers have no pending factors any more; re-arm the list
 __global__ void k_flush_done(DevState S, const int *__restrict__ list, int *count_ptr, int count_fixed) {
     const int count = count_ptr ? *count_ptr : count_fixed;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x)
-        S.fcnt[list ? list[e] : e] = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const int w = list ? list[e] : e;
+        S.fcnt[2 * w] = 0;
+        S.fcnt[2 * w + 1] = 0;
+    }
     if (count_ptr && blockIdx.x == 0 && threadIdx.x == 0) {
         S.upd_moves[1] += (unsigned long long)count;      // walkers flushed
     }
@@ -313,7 +322,7 @@ k_measure_delayed(DevState S, double *__restrict__ ol_out, int accumulate) {
     const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= S.nw) return;
-    const int ns = S.ns, cnt = S.fcnt[w];
+    const int ns = S.ns, cnt = S.fcnt[2 * w];
     const int *kup = S.kup + (size_t)w * ns;
     const int *kdn = S.kdn + (size_t)w * ns;
     const double *Wu = S.W_up + (size_t)w * ns * S.n_up, *Wd = S.W_dn + (size_t)w * ns * S.n_dn;

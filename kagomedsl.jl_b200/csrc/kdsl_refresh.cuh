@@ -132,7 +132,8 @@ __global__ void k_refresh_status(DevState S, const int *__restrict__ list, const
     } else {
         atomicAnd(&S.flags[w], ~KDSL_FLAG_SINGULAR_DEV);
         S.n_refresh[w] += 1ull;
-        S.fcnt[w] = 0;                                        // W0 is now exact: drop the pending factors
+        S.fcnt[2 * w] = 0;                                    // W0 is now exact: drop the pending updates
+        S.fcnt[2 * w + 1] = 0;
     }
 }
 

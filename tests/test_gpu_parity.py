@@ -97,11 +97,11 @@ def test_update_W_matches_oracle_and_formula(kd):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [2, 1, 0])
 @pytest.mark.parametrize("n1,n2,nw,n_sweeps", [(2, 2, 8, 600), (4, 3, 8, 1500), (6, 6, 6, 2500)])
 def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps, variant):
     """replayed (r, bond) sequence: kappa, Z, acceptance counters bit-exact; W within 1e-10.
-    variant 1 = delayed rank-k updates (default), 0 = immediate rank-1 update like the reference"""
+    variant 2 = delayed updates in Woodbury form (default), 1 = delayed factor lists, 0 = immediate rank-1 update like the reference"""
     PBC, anti = ((False, False), (False, False)) if n1 == 2 else ((True, True), (True, False))
     lat, ham = U.problem(n1, n2, PBC, anti)
     ns = kd.ns(lat)
@@ -145,7 +145,7 @@ def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps, variant):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [2, 1, 0])
 def test_device_rng_matches_xoshiro_stream(kd, variant):
     """device-drawn random numbers follow Julia's Xoshiro256++ conventions: same
     trajectory and same final generator state as the oracle fed with the same initial states"""
@@ -195,8 +195,9 @@ def test_measure_matches_oracle_getOL(kd):
     eng.close()
 
 
-def test_measure_with_pending_factors(kd):
-    """O_L evaluated from W0 + pending delayed factors equals the oracle's O_L on the same trajectory"""
+@pytest.mark.parametrize("variant", [2, 1])
+def test_measure_with_pending_factors(kd, variant):
+    """O_L evaluated from W0 + pending delayed updates equals the oracle's O_L on the same trajectory"""
     lat, ham = U.problem(4, 3)
     ns, nw, n = kd.ns(lat), 8, 17                      # 17 sweeps: no refresh since sweep 0, factors pending
     rng = np.random.default_rng(77)
@@ -204,6 +205,7 @@ def test_measure_with_pending_factors(kd):
     r = rng.random((n, nw)) * 0.3                       # small r: many acceptances
     bond = rng.integers(1, len(ham.nn) + 1, size=(n, nw)).astype(np.int32)
     eng = kd.Engine(ham, nw)
+    eng.set_option("update_variant", variant)
     eng.set_config(ku, kdn)
     eng.refresh()
     eng.sweeps = 1
