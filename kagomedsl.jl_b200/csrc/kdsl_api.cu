@@ -60,6 +60,7 @@ struct kdsl_handle_s {
     double *A_up = nullptr, *A_dn = nullptr;
     int *status = nullptr;
     int *colsrc = nullptr;        // [nw][2][Np] column map of the pivoted inverse
+    int *urow = nullptr;          // [nw][2][ns] sites not occupied by the species (non-trivial rows of W)
     int Np_up = 0, Np_dn = 0;     // tilde_U dimensions padded to a multiple of 8
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
@@ -205,7 +206,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
     {
         Span sp(h, KDSL_T_REFRESH_GATHER);
         if (fast)
-            k_gather_tilde_padded<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->Np_up, h->Np_dn);
+            k_gather_tilde_padded<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->Np_up, h->Np_dn, h->urow, S.ns);
         else
             k_gather_tilde<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
         CK(cudaGetLastError());
@@ -231,10 +232,11 @@ int launch_refresh(kdsl_handle h, const int *list) {
         Span sp(h, KDSL_T_REFRESH_GEMM);
         if (fast) {
             constexpr int KT = 24;
-            const int tiles = ((S.ns + 71) / 72) * ((Nmax + 71) / 72);
+            const int Mmax = S.ns - std::min(S.n_up, S.n_dn);
+            const int tiles = ((Mmax + 71) / 72) * ((Nmax + 71) / 72);
             const size_t smem = (size_t)4 * 72 * KT * sizeof(double);
             CK(cudaFuncSetAttribute(k_gemm_W_dmma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn));
+            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn), h->urow, S.ns);
         } else {
             constexpr int BM = 64, BN = 64;
             const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
@@ -512,6 +514,7 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
     ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
+    ALLOC(h->urow, 2 * nw * ns);
     ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
 #undef ALLOC
     // default xoshiro states must not be all-zero: seed walker w with a fixed SplitMix64 stream

@@ -31,8 +31,11 @@ __device__ __forceinline__ int frag_idx(int r, int k, int KT) {
 // grid (nw, 2); dynamic smem N ints.
 __global__ void __launch_bounds__(256)
 k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restrict__ A_up,
-                      double *__restrict__ A_dn, int *__restrict__ status, int Np_up, int Np_dn) {
+                      double *__restrict__ A_dn, int *__restrict__ status, int Np_up, int Np_dn,
+                      int *__restrict__ urow_base, int urow_stride) {
     extern __shared__ int s_site[];
+    __shared__ int s_wsum[8];
+    __shared__ int s_base;
     const int b = blockIdx.x, spin = blockIdx.y;
     if (b >= batch_count(S, list)) return;
     const int w = list ? list[b] : b;
@@ -44,7 +47,7 @@ k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restri
         const int l = kap[R];
         if (l != 0) s_site[l - 1] = R;
     }
-    if (threadIdx.x == 0) status[2 * b + spin] = 0;
+    if (threadIdx.x == 0) { status[2 * b + spin] = 0; s_base = 0; }
     __syncthreads();
     for (int e = threadIdx.x; e < Np * Np; e += blockDim.x) {
         const int c = e / Np, l = e - c * Np;
@@ -52,6 +55,26 @@ k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restri
         if (c < N && l < N) v = U[(size_t)c * ns + s_site[l]];      // tilde_U[l, c] = U[R_l, c]
         else v = (c == l) ? 1.0 : 0.0;
         A[e] = v;
+    }
+    // ordered list of the sites NOT occupied by this species (the non-trivial rows of W)
+    int *urow = urow_base + ((size_t)2 * b + spin) * urow_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s0 = 0; s0 < ns; s0 += 256) {
+        const int site = s0 + threadIdx.x;
+        const bool un = site < ns && kap[site] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, un);
+        if (lane == 0) s_wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int q = 0; q < warp; q++) off += s_wsum[q];
+        if (un) urow[off + __popc(m & ((1u << lane) - 1u))] = site;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int q = 0; q < 8; q++) t += s_wsum[q];
+            s_base += t;
+        }
+        __syncthreads();
     }
 }
 
@@ -371,34 +394,42 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
     for (int j = tid; j < Np; j += T) colsrc[j] = sC[j];
 }
 
-// W[w] (ns x N) = U (ns x N) * X,  X[:, j] = R[:, colsrc[j]] (R stored with leading dimension Np).
+// W[w][unoccupied sites, :] = U[unoccupied sites, :] * X,  X[:, j] = R[:, colsrc[j]] (R stored with leading
+// dimension Np); rows of W on occupied sites are the unit vectors e_l (SURVEY 8(a) invariant) and are written by
+// the CTA whose row tile spans them, so that every 32-byte sector is completed by one CTA.
 // grid (tiles_m * tiles_n, nw, 2), 288 threads = 9 warps in a 3x3 arrangement of 24x24 warp tiles.
 template <int KT>
 __global__ void __launch_bounds__(288, 2)
 k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict__ X_up,
               const double *__restrict__ X_dn, const int *__restrict__ status,
-              const int *__restrict__ colsrc_base, int Np_up, int Np_dn, int cs_stride) {
+              const int *__restrict__ colsrc_base, int Np_up, int Np_dn, int cs_stride,
+              const int *__restrict__ urow_base, int urow_stride) {
     constexpr int TM = 72, TN = 72, NT = 288;
     extern __shared__ double gsm[];
     double (*sA)[TM * KT] = reinterpret_cast<double (*)[TM * KT]>(gsm);
     double (*sB)[TN * KT] = reinterpret_cast<double (*)[TN * KT]>(gsm + 2 * TM * KT);
     __shared__ int sSrc[TN];
+    __shared__ int sRowSite[TM + 1];
     const int b = blockIdx.y, spin = blockIdx.z;
     if (b >= batch_count(S, list)) return;
     if (status[2 * b] | status[2 * b + 1]) return;
     const int w = list ? list[b] : b;
     const int ns = S.ns, N = spin ? S.n_dn : S.n_up, Np = spin ? Np_dn : Np_up;
-    const int tiles_m = (ns + TM - 1) / TM;
+    const int M = ns - N;                                  // unoccupied sites of this species
+    const int tiles_m = (M + TM - 1) / TM;
     const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
     const int m0 = tm * TM, n0 = tn * TN;
     if (n0 >= N) return;
     const double *U = spin ? S.U_dn : S.U_up;
     const double *X = (spin ? X_dn : X_up) + (size_t)b * Np * Np;
     const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
+    const int *urow = urow_base + ((size_t)2 * b + spin) * urow_stride;
+    const int *kap = (spin ? S.kdn : S.kup) + (size_t)w * ns;
     double *W = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % 3, wn = warp / 3;
     if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
+    if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
     __syncthreads();
 
     constexpr int PER = TM * KT / NT;                  // elements of each operand per thread per stage
@@ -408,8 +439,9 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
 #pragma unroll
         for (int q = 0; q < PER; q++) {
             const int e = tid + q * NT;
-            const int r = e % TM, k = e / TM;                      // A: coalesced along rows
-            ra[q] = (m0 + r < ns && kk + k < N) ? U[(size_t)(kk + k) * ns + m0 + r] : 0.0;
+            const int r = e % TM, k = e / TM;                      // A: gathered rows of U
+            const int site = sRowSite[r];
+            ra[q] = (site >= 0 && kk + k < N) ? U[(size_t)(kk + k) * ns + site] : 0.0;
             const int kb = e % KT, n = e / KT;                     // B: contiguous along k
             const int src = sSrc[n];
             rb[q] = (src >= 0 && kk + kb < N) ? X[(size_t)src * Np + kk + kb] : 0.0;
@@ -461,9 +493,19 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
             if (n >= N) continue;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                const int m = m0 + 24 * wm + 8 * i + gr;
-                if (m < ns) W[(size_t)n * ns + m] = c[i][j][e];
+                const int site = sRowSite[24 * wm + 8 * i + gr];
+                if (site >= 0) W[(size_t)n * ns + site] = c[i][j][e];
             }
         }
+    }
+    // unit rows of the occupied sites inside this tile's site range [s_lo, s_hi)
+    const int s_lo = (tm == 0) ? 0 : sRowSite[0];
+    const int s_hi = (tm == tiles_m - 1 || sRowSite[TM] < 0) ? ns : sRowSite[TM];
+    const int ncols = min(TN, N - n0);
+    for (int x = tid; x < (s_hi - s_lo) * ncols; x += NT) {
+        const int sidx = x % (s_hi - s_lo), cc = x / (s_hi - s_lo);
+        const int site = s_lo + sidx;
+        const int l = kap[site];
+        if (l != 0) W[(size_t)(n0 + cc) * ns + site] = (l - 1 == n0 + cc) ? 1.0 : 0.0;
     }
 }
