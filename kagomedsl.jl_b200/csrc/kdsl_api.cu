@@ -16,6 +16,8 @@
 #include "kdsl_propose.cuh"
 #include "kdsl_refresh.cuh"
 #include "kdsl_refresh_fast.cuh"
+#include "kdsl_inverse_v3.cuh"
+#include "kdsl_inverse_v4.cuh"
 #include "kdsl_delayed.cuh"
 #include "kdsl_woodbury.cuh"
 #include "kdsl_update.cuh"
@@ -184,8 +186,45 @@ int launch_inverse_blocked(kdsl_handle h, const int *list, double *A, int spin, 
     return KDSL_OK;
 }
 
-// one CTA per matrix and ONE CTA per SM: 148 x N^2 x 8 B of live matrices stay L2 resident
+template <int NB, int RPT, int T>
+int launch_inverse_v3(kdsl_handle h, const int *list, double *A, int spin, int Np) {
+    constexpr int NWARP = T / 32;
+    const size_t smem = ((size_t)3 * NB * Np + 5 * NB * NB + 2 * NWARP + 2 * NWARP) * sizeof(double) +
+                        ((size_t)2 * NWARP + 3 * Np + 5 * NB) * sizeof(int);
+    CK(cudaFuncSetAttribute(k_inverse_v3<NB, RPT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_v3<NB, RPT, T><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
+template <int NB, int RPT, int T>
+int launch_inverse_v4(kdsl_handle h, const int *list, double *A, int spin, int Np) {
+    constexpr int NWARP = T / 32;
+    const size_t smem = ((size_t)2 * NB * Np + 2 * NWARP * NB + 2 * NWARP + 2 * NWARP) * sizeof(double) +
+                        ((size_t)2 * NWARP + NB) * sizeof(int);
+    CK(cudaFuncSetAttribute(k_inverse_v4<NB, RPT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_v4<NB, RPT, T><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
+    if (h->inverse_variant == 0) {
+        // implicit-pivoting blocked Gauss-Jordan, one CTA per matrix and ONE CTA per SM (matrices stay L2 resident)
+        if (Np <= 256) return h->inverse_tuning == 1 ? launch_inverse_v4<24, 1, 256>(h, list, A, spin, Np)
+                                                     : launch_inverse_v4<32, 1, 256>(h, list, A, spin, Np);
+        if (Np <= 512) return launch_inverse_v4<24, 2, 256>(h, list, A, spin, Np);
+        if (Np <= 1024) return launch_inverse_v4<8, 4, 256>(h, list, A, spin, Np);
+        return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
+    }
+    if (h->inverse_variant == 3) {
+        // one CTA per matrix and ONE CTA per SM: 148 x N^2 x 8 B of live matrices stay L2 resident
+        if (Np <= 256) return h->inverse_tuning == 1 ? launch_inverse_v3<24, 1, 512>(h, list, A, spin, Np)
+                                                     : launch_inverse_v3<32, 1, 512>(h, list, A, spin, Np);
+        if (Np <= 512) return launch_inverse_v3<16, 1, 512>(h, list, A, spin, Np);
+        if (Np <= 1024) return launch_inverse_v3<8, 2, 512>(h, list, A, spin, Np);
+        return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
+    }
     const int v = h->inverse_tuning;
     if (Np <= 256) {
         if (v == 1) return launch_inverse_blocked<24, 1, 256, 2>(h, list, A, spin, Np);
@@ -202,7 +241,7 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
 int launch_refresh(kdsl_handle h, const int *list) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
-    const bool fast = h->inverse_variant == 0;
+    const bool fast = h->inverse_variant != 1;
     {
         Span sp(h, KDSL_T_REFRESH_GATHER);
         if (fast)
@@ -236,7 +275,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
             const int tiles = ((Mmax + 71) / 72) * ((Nmax + 71) / 72);
             const size_t smem = (size_t)4 * 72 * KT * sizeof(double);
             CK(cudaFuncSetAttribute(k_gemm_W_dmma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn), h->urow, S.ns);
+            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn), h->urow, S.ns, h->inverse_variant == 0 ? 1 : 0);
         } else {
             constexpr int BM = 64, BN = 64;
             const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);

@@ -395,7 +395,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
 }
 
 // W[w][unoccupied sites, :] = U[unoccupied sites, :] * X,  X[:, j] = R[:, colsrc[j]] (R stored with leading
-// dimension Np); rows of W on occupied sites are the unit vectors e_l (SURVEY 8(a) invariant) and are written by
+// dimension Np; with perm_k the stored rows are permuted as well: X[k, j] = R[rho, colsrc[j]], k = colsrc[rho]); rows of W on occupied sites are the unit vectors e_l (SURVEY 8(a) invariant) and are written by
 // the CTA whose row tile spans them, so that every 32-byte sector is completed by one CTA.
 // grid (tiles_m * tiles_n, nw, 2), 288 threads = 9 warps in a 3x3 arrangement of 24x24 warp tiles.
 template <int KT>
@@ -403,13 +403,14 @@ __global__ void __launch_bounds__(288, 2)
 k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict__ X_up,
               const double *__restrict__ X_dn, const int *__restrict__ status,
               const int *__restrict__ colsrc_base, int Np_up, int Np_dn, int cs_stride,
-              const int *__restrict__ urow_base, int urow_stride) {
+              const int *__restrict__ urow_base, int urow_stride, int perm_k) {
     constexpr int TM = 72, TN = 72, NT = 288;
     extern __shared__ double gsm[];
     double (*sA)[TM * KT] = reinterpret_cast<double (*)[TM * KT]>(gsm);
     double (*sB)[TN * KT] = reinterpret_cast<double (*)[TN * KT]>(gsm + 2 * TM * KT);
     __shared__ int sSrc[TN];
     __shared__ int sRowSite[TM + 1];
+    __shared__ int sKp[1024];                              // contraction index -> column of U (implicit-pivoting inverse)
     const int b = blockIdx.y, spin = blockIdx.z;
     if (b >= batch_count(S, list)) return;
     if (status[2 * b] | status[2 * b + 1]) return;
@@ -430,6 +431,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     const int wm = warp % 3, wn = warp / 3;
     if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
     if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
+    for (int k = tid; k < N; k += NT) sKp[k] = perm_k ? colsrc[k] : k;
     __syncthreads();
 
     constexpr int PER = TM * KT / NT;                  // elements of each operand per thread per stage
@@ -441,7 +443,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
             const int e = tid + q * NT;
             const int r = e % TM, k = e / TM;                      // A: gathered rows of U
             const int site = sRowSite[r];
-            ra[q] = (site >= 0 && kk + k < N) ? U[(size_t)(kk + k) * ns + site] : 0.0;
+            ra[q] = (site >= 0 && kk + k < N) ? U[(size_t)sKp[kk + k] * ns + site] : 0.0;
             const int kb = e % KT, n = e / KT;                     // B: contiguous along k
             const int src = sSrc[n];
             rb[q] = (src >= 0 && kk + kb < N) ? X[(size_t)src * Np + kk + kb] : 0.0;

@@ -6,11 +6,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 nw = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 lat = kd.DoubleKagome(1.0, n, n, (True, True), (True, False)); ns = kd.ns(lat)
 ham = kd.Hamiltonian(ns // 2, ns // 2, lat); ku, kdn = kd.init_conf_qr(ham, ns, ns // 2)
-eng = kd.Engine(ham, nw, 0); eng.set_config(ku, kdn); eng.refresh()
+eng = kd.Engine(ham, nw, 0); eng.set_option('inverse_variant', 1); eng.set_config(ku, kdn); eng.refresh()
 W_ref = eng.get_W(3, 1).copy()
 out = (C.c_longlong * 8)()
 names = ["1 panel load", "2 panel LU", "3 publish+moves", "4 columns (U_K, pivot rows)", "5 panel cols", "6 GEMM update"]
-for tuning in (0, 1, 2, 3):
+# (variant 0 = k_inverse_v4 has four phases: load, pivot loop, publish + gather, GEMM update)
+for variant, tuning in ((0, 0), (0, 1), (3, 0), (2, 1)):
+    eng.set_option("inverse_variant", variant)
     eng.set_option("inverse_tuning", tuning)
     eng.refresh()
     eng._L.kdsl_debug_inverse_phases(eng._h, out)
@@ -19,6 +21,6 @@ for tuning in (0, 1, 2, 3):
     eng._L.kdsl_debug_inverse_phases(eng._h, out)
     v = np.array(out[:6], dtype=float) / 2     # two launches (up, down)
     err = np.abs(eng.get_W(3, 1) - W_ref).max()
-    print("tuning %d: cycles per matrix (CTA 0) total %.0f  |dW| vs tuning0 %.2e" % (tuning, v.sum(), err))
+    print("variant %d tuning %d: cycles per matrix (CTA 0) total %.0f  |dW| vs first %.2e" % (variant, tuning, v.sum(), err))
     print("   " + "  ".join("%s=%.0f" % (nme.split()[0] + nme.split()[1][:5], c) for nme, c in zip(names, v)))
     print("   ", {k: round(x["ms"], 3) for k, x in eng.timers().items() if x["ms"] > 0})
