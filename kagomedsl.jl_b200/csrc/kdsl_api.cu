@@ -197,13 +197,12 @@ int launch_inverse_v3(kdsl_handle h, const int *list, double *A, int spin, int N
     return KDSL_OK;
 }
 
-template <int NB, int RPT, int T>
+template <int NB, int RPT, int T, int TP>
 int launch_inverse_v4(kdsl_handle h, const int *list, double *A, int spin, int Np) {
-    constexpr int NWARP = T / 32;
-    const size_t smem = ((size_t)2 * NB * Np + 2 * NWARP * NB + 2 * NWARP + 2 * NWARP) * sizeof(double) +
-                        ((size_t)2 * NWARP + NB) * sizeof(int);
-    CK(cudaFuncSetAttribute(k_inverse_v4<NB, RPT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_inverse_v4<NB, RPT, T><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    static_assert(RPT * TP >= 8 && TP <= 256, "rows per CTA");
+    const size_t smem = ((size_t)2 * NB * Np + NB + 2) * sizeof(double) + ((size_t)12 + NB) * sizeof(int);
+    CK(cudaFuncSetAttribute(k_inverse_v4<NB, RPT, T, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_v4<NB, RPT, T, TP><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
     CK(cudaGetLastError());
     return KDSL_OK;
 }
@@ -211,10 +210,14 @@ int launch_inverse_v4(kdsl_handle h, const int *list, double *A, int spin, int N
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     if (h->inverse_variant == 0) {
         // implicit-pivoting blocked Gauss-Jordan, one CTA per matrix and ONE CTA per SM (matrices stay L2 resident)
-        if (Np <= 256) return h->inverse_tuning == 1 ? launch_inverse_v4<24, 1, 256>(h, list, A, spin, Np)
-                                                     : launch_inverse_v4<32, 1, 256>(h, list, A, spin, Np);
-        if (Np <= 512) return launch_inverse_v4<24, 2, 256>(h, list, A, spin, Np);
-        if (Np <= 1024) return launch_inverse_v4<8, 4, 256>(h, list, A, spin, Np);
+        if (Np <= 256) {
+            if (h->inverse_tuning == 1) return launch_inverse_v4<24, 1, 256, 256>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 2) return launch_inverse_v4<24, 2, 256, 128>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 3) return launch_inverse_v4<32, 2, 256, 128>(h, list, A, spin, Np);
+            return launch_inverse_v4<32, 1, 256, 256>(h, list, A, spin, Np);
+        }
+        if (Np <= 512) return launch_inverse_v4<24, 2, 256, 256>(h, list, A, spin, Np);
+        if (Np <= 1024) return launch_inverse_v4<8, 4, 256, 256>(h, list, A, spin, Np);
         return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
     }
     if (h->inverse_variant == 3) {

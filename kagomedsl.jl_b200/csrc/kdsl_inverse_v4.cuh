@@ -7,8 +7,8 @@
 //   2. kw in-place rank-1 Gauss-Jordan steps on the panel.  The pivot of step k is the largest |.| of the current
 //      column over the rows that were never a pivot (LAPACK's rule; an exactly zero / non-finite pivot => singular);
 //      rows are NOT exchanged.  The register file rotates by one column per step so the loop body is identical
-//      for every k (rolled loop, ~NB DFMAs), and there is ONE block barrier per pivot: every warp posts its best
-//      candidate together with that candidate's panel row, after the barrier every thread picks the winner itself;
+//      for every k (rolled loop, ~NB DFMAs); two block barriers per pivot (keys, then the winning row), see below;
+//      the search compares the top 32 bits of |x| (ties within 2^-17 relative go to the lowest row);
 //   3. the finished panel columns R (= the final values of these columns for this block step) are written back,
 //      R - E (E = 1 at (pivot row of step q, column q)) goes to shared memory in DMMA fragment order, and the raw
 //      pivot rows X = A[p_q, :] of all other columns are gathered;
@@ -20,11 +20,13 @@
 #include "kdsl_refresh.cuh"
 #include "kdsl_refresh_fast.cuh"
 
-template <int NB, int RPT, int T>
+// T threads per CTA; the first TP of them own RPT matrix rows each during the panel factorisation (a pivot row is
+// broadcast through shared memory: fewer, fatter threads read it less often).
+template <int NB, int RPT, int T, int TP>
 __global__ void __launch_bounds__(T, 1)
 k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
              int *__restrict__ status, int *__restrict__ colsrc_base, int Np, int cs_stride) {
-    constexpr int NWARP = T / 32;
+    constexpr int NWARP = T / 32, PWARP = TP / 32;
     constexpr int KS = NB / 4;                          // DMMA k-steps per panel
     constexpr int CT = 3;                               // column tiles per warp work item
     static_assert(NB % 8 == 0, "panel width must be a multiple of 8");
@@ -33,16 +35,18 @@ k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
     if (b >= batch_count(S, list)) return;
     double *sM = sm;                                    // [Np x NB] frag-major (r = row, k = q): R - E
     double *sX = sM + (size_t)NB * Np;                  // [Np x NB] frag-major (r = column j, k = q): A[p_q, j]
-    double *sRow = sX + (size_t)NB * Np;                // [2][NWARP][NB] candidate pivot rows
-    double *sRinv = sRow + 2 * NWARP * NB;              // [2][NWARP]
-    unsigned long long *sKey = reinterpret_cast<unsigned long long *>(sRinv + 2 * NWARP);   // [2][NWARP]
-    int *sIdx = reinterpret_cast<int *>(sKey + 2 * NWARP);                                  // [2][NWARP]
-    int *sPivRow = sIdx + 2 * NWARP;                    // [NB] pivot row of each step of the current panel
+    double *sRow = sX + (size_t)NB * Np;                // [NB] the pivot row of the current step
+    double *sRinv = sRow + NB;                          // [2] reciprocal pivot
+    unsigned *sKey = reinterpret_cast<unsigned *>(sRinv + 2);   // [8] per-warp candidate keys (16-byte aligned)
+    int *sIdx = reinterpret_cast<int *>(sKey + 8);      // [4] pivot row
+    int *sPivRow = sIdx + 4;                            // [NB] pivot row of each step of the current panel
+    static_assert(PWARP <= 8 && TP <= T, "the warp index is folded into 3 key bits");
 
     double *A = A_base + (size_t)b * Np * Np;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gr = lane >> 2, tg = lane & 3;
-    unsigned pivmask = 0u;                              // bit r: my row (tid + T r) has been a pivot
+    const bool owner = tid < TP;                        // this thread owns rows tid + TP r
+    unsigned pivmask = 0u;                              // bit r: my row (tid + TP r) has been a pivot
     int gstep[RPT];                                     // ... and at which elimination step
 #pragma unroll
     for (int r = 0; r < RPT; r++) gstep[r] = 0;
@@ -55,42 +59,82 @@ k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
         int mypiv[RPT];
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
-            const int i = tid + T * r;
+            const int i = tid + TP * r;
             mypiv[r] = -1;
 #pragma unroll
-            for (int c = 0; c < NB; c++) a[r][c] = (i < Np && c < kw) ? A[(size_t)(k0 + c) * Np + i] : 0.0;
+            for (int c = 0; c < NB; c++) a[r][c] = (owner && i < Np && c < kw) ? A[(size_t)(k0 + c) * Np + i] : 0.0;
         }
         PHASE_TICK(0);
-        // ---- 2. kw in-place Gauss-Jordan steps; the current column is always a[.][0] ----
+        // ---- 2. kw in-place Gauss-Jordan steps; the current column is always a[.][0].
+        // Two barriers per pivot: (1) every warp posts a 32-bit key of its best candidate, (2) the owner of the
+        // winning row posts that row.  Only the NEXT column is updated right after the second barrier; the other
+        // NB-2 columns of step k are updated in iteration k+1, where their DFMAs overlap the latency of the warp
+        // reduction and of the reciprocal (software pipelining by hand; a warp issues in order). ----
+        double tail[RPT];                               // pending: -l of my row (pivot row: 1/pivot)
+        bool pend = false;
+        unsigned pend_p = 0u;                           // bit r: my row r was the pivot of the pending step
+        auto apply_pending = [&]() {                    // columns 2.. of the pending step (sRow still holds its pivot row)
+            if (!owner) return;
+            const double2 *prow2 = reinterpret_cast<const double2 *>(sRow);
+#pragma unroll
+            for (int j = 2; j < NB; j += 2) {
+                const double2 pv = prow2[j >> 1];
+#pragma unroll
+                for (int r = 0; r < RPT; r++) {
+                    if ((pend_p >> r) & 1u) {
+                        a[r][j - 1] = a[r][j] * tail[r];
+                        a[r][j] = a[r][j + 1 < NB ? j + 1 : j] * tail[r];
+                    } else {
+                        a[r][j - 1] = fma(tail[r], pv.x, a[r][j]);
+                        a[r][j] = fma(tail[r], pv.y, a[r][j + 1 < NB ? j + 1 : j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; r++) a[r][NB - 1] = tail[r];
+        };
 #pragma unroll 1
         for (int k = 0; k < kw; k++) {
-            const int par = k & 1;
-            unsigned long long key = 0ull;
-            int bi = -1, br = 0;
+            // candidate of this thread: largest |a[r][0]| over its never-pivoted rows (top 32 bits of |x|)
+            unsigned hi = 0u;
+            int br = 0;
+            bool valid = false;
             double bval = 1.0;
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
-                const int i = tid + T * r;
-                if (i < Np && !((pivmask >> r) & 1u)) {
+                const int i = tid + TP * r;
+                if (owner && i < Np && !((pivmask >> r) & 1u)) {
                     const double v = a[r][0];
-                    const unsigned long long kk = (unsigned long long)__double_as_longlong(fabs(v));
-                    if (bi < 0 || kk > key) { key = kk; bi = i; br = r; bval = v; }
+                    const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
+                    if (!valid || h > hi) { hi = h; br = r; bval = v; }
+                    valid = true;
                 }
             }
-            const double my_rinv = 1.0 / bval;          // speculative: off the critical path of the search
-            const bool valid = bi >= 0;
-            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
             const unsigned mhi = __reduce_max_sync(0xffffffffu, valid ? hi : 0u);
-            const bool c1 = valid && hi == mhi;
-            const unsigned mlo = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
-            const unsigned win = __ballot_sync(0xffffffffu, c1 && lo == mlo);
-            if (win == 0u) {
-                if (lane == 0) { sKey[par * NWARP + warp] = 0ull; sIdx[par * NWARP + warp] = -1; }
-            } else if (lane == __ffs(win) - 1) {        // lowest row among the warp's maxima
-                sKey[par * NWARP + warp] = key;
-                sIdx[par * NWARP + warp] = bi;
-                sRinv[par * NWARP + warp] = my_rinv;
-                double2 *dst = reinterpret_cast<double2 *>(sRow + (size_t)(par * NWARP + warp) * NB);
+            double my_rinv = 1.0 / bval;                // speculative; LAPACK getf2 scales by the reciprocal pivot
+            asm volatile("" : "+d"(my_rinv));           // keep it here (ptxas would sink it behind the first barrier)
+            if (pend) apply_pending();
+            const unsigned win = __ballot_sync(0xffffffffu, valid && hi == mhi);
+            const bool leader = win != 0u && lane == __ffs(win) - 1;      // lowest row among the warp's maxima
+            if (lane == 0 && warp < 8) sKey[warp] = (win != 0u) ? ((mhi & 0xfffffff8u) | (unsigned)(7 - warp)) : 0u;
+            __syncthreads();
+            unsigned bk = 0u;
+            {
+                const uint4 k0v = *reinterpret_cast<const uint4 *>(sKey);
+                const uint4 k1v = *reinterpret_cast<const uint4 *>(sKey + 4);
+                bk = max(max(max(k0v.x, k0v.y), max(k0v.z, k0v.w)), max(max(k1v.x, k1v.y), max(k1v.z, k1v.w)));
+            }
+            if ((bk >> 3) == 0u || bk >= 0x7ff00000u) {  // zero (below 2^-1039) / non-finite pivot: singular
+                if (tid == 0) status[2 * b + spin] = 1;
+                return;
+            }
+            const int wq = 7 - (int)(bk & 7u);           // ties within 2^-17 relative: the lowest warp
+            if (warp == wq && leader) {
+                const int i = tid + TP * br;
+                sIdx[0] = i;
+                sPivRow[k] = i;
+                sRinv[0] = my_rinv;
+                double2 *dst = reinterpret_cast<double2 *>(sRow);
 #pragma unroll
                 for (int j = 0; j < NB; j += 2) {
                     double x0 = a[0][j], x1 = a[0][j + 1];
@@ -100,53 +144,35 @@ k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
                 }
             }
             __syncthreads();
-            unsigned long long bk = 0ull;
-            int bq = 0;
-#pragma unroll
-            for (int q = 0; q < NWARP; q++) {
-                const unsigned long long ok = sKey[par * NWARP + q];
-                if (ok > bk) { bk = ok; bq = q; }        // ties: the lowest warp = the lowest row
-            }
-            if (bk == 0ull || bk >= 0x7ff0000000000000ull) {   // exact-zero / non-finite pivot
-                if (tid == 0) status[2 * b + spin] = 1;
-                return;
-            }
-            const int p = sIdx[par * NWARP + bq];
-            const double rinv = sRinv[par * NWARP + bq];
-            const double2 *prow2 = reinterpret_cast<const double2 *>(sRow + (size_t)(par * NWARP + bq) * NB);
-            double prow[NB];
-#pragma unroll
-            for (int j = 0; j < NB; j += 2) {
-                const double2 v = prow2[j >> 1];
-                prow[j] = v.x; prow[j + 1] = v.y;
-            }
+            const int p = sIdx[0];
+            const double rinv = sRinv[0];
+            const double prow1 = sRow[1];
+            pend_p = 0u;
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
-                const int i = tid + T * r;
-                if (i == p) {
+                const int i = tid + TP * r;
+                if (owner && i == p) {
                     pivmask |= 1u << r;
+                    pend_p |= 1u << r;
                     gstep[r] = k0 + k;
                     mypiv[r] = k;
-                    sPivRow[k] = i;
-#pragma unroll
-                    for (int j = 1; j < NB; j++) a[r][j - 1] = a[r][j] * rinv;
-                    a[r][NB - 1] = rinv;
+                    tail[r] = rinv;
+                    a[r][0] = a[r][1] * rinv;
                 } else {
-                    const double l = a[r][0] * rinv;
-                    const double nl = -l;
-#pragma unroll
-                    for (int j = 1; j < NB; j++) a[r][j - 1] = fma(nl, prow[j], a[r][j]);
-                    a[r][NB - 1] = nl;
+                    tail[r] = -(a[r][0] * rinv);
+                    a[r][0] = fma(tail[r], prow1, a[r][1]);
                 }
             }
+            pend = true;
         }
+        if (pend) apply_pending();
         PHASE_TICK(1);
         // ---- 3. write the finished panel columns; R - E to shared memory (fragment order) ----
         // after kw rotations register slot cs holds panel column (cs + kw) mod NB (columns >= kw are zero padding)
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
-            const int i = tid + T * r;
-            if (i < Np) {
+            const int i = tid + TP * r;
+            if (owner && i < Np) {
 #pragma unroll
                 for (int cs = 0; cs < NB; cs += 4) {
                     int col = cs + kw;
@@ -168,10 +194,8 @@ k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
         }
         __syncthreads();                                // sPivRow complete
         // ---- 4. raw pivot rows of the other columns ----
-#pragma unroll
-        for (int r = 0; r < RPT; r++) {
-            const int j = tid + T * r;
-            if (j < Np && !(j >= k0 && j < k0 + kw)) {
+        for (int j = tid; j < Np; j += T) {
+            if (!(j >= k0 && j < k0 + kw)) {
                 const double *col = A + (size_t)j * Np;
 #pragma unroll
                 for (int q = 0; q < NB; q += 4) {
@@ -246,7 +270,7 @@ k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
     int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
 #pragma unroll
     for (int r = 0; r < RPT; r++) {
-        const int i = tid + T * r;
-        if (i < Np) colsrc[i] = gstep[r];
+        const int i = tid + TP * r;
+        if (owner && i < Np) colsrc[i] = gstep[r];
     }
 }

@@ -11,7 +11,7 @@ W_ref = eng.get_W(3, 1).copy()
 out = (C.c_longlong * 8)()
 names = ["1 panel load", "2 panel LU", "3 publish+moves", "4 columns (U_K, pivot rows)", "5 panel cols", "6 GEMM update"]
 # (variant 0 = k_inverse_v4 has four phases: load, pivot loop, publish + gather, GEMM update)
-for variant, tuning in ((0, 0), (0, 1), (3, 0), (2, 1)):
+for variant, tuning in ((0, 0), (0, 1), (0, 2), (0, 3)):
     eng.set_option("inverse_variant", variant)
     eng.set_option("inverse_tuning", tuning)
     eng.refresh()
