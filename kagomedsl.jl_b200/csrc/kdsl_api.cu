@@ -80,6 +80,7 @@ struct kdsl_handle_s {
     int64_t refresh_every = 0;
     int update_variant = 2, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
     int since_flush = 0;
+    int fuse_sweeps = 1;          // fuse consecutive proposals into one launch where the loop allows it
     int inverse_tuning = 0;
     int update_ch = 8;
     // profiling
@@ -211,10 +212,9 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
     if (h->inverse_variant == 0) {
         // implicit-pivoting blocked Gauss-Jordan, one CTA per matrix and ONE CTA per SM (matrices stay L2 resident)
         if (Np <= 256) {
-            if (h->inverse_tuning == 1) return launch_inverse_v4<24, 1, 256, 256>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 1) return launch_inverse_v4<32, 1, 256, 256>(h, list, A, spin, Np);
             if (h->inverse_tuning == 2) return launch_inverse_v4<24, 2, 256, 128>(h, list, A, spin, Np);
-            if (h->inverse_tuning == 3) return launch_inverse_v4<32, 2, 256, 128>(h, list, A, spin, Np);
-            return launch_inverse_v4<32, 1, 256, 256>(h, list, A, spin, Np);
+            return launch_inverse_v4<24, 1, 256, 256>(h, list, A, spin, Np);
         }
         if (Np <= 512) return launch_inverse_v4<24, 2, 256, 256>(h, list, A, spin, Np);
         if (Np <= 1024) return launch_inverse_v4<8, 4, 256, 256>(h, list, A, spin, Np);
@@ -334,23 +334,32 @@ int ensure_replay_capacity(kdsl_handle h, size_t n) {
 }
 
 // the lock-step Carlo loop: n x { sweep!; ctx.sweeps += 1; [measure!] }
+// In Woodbury mode consecutive sweeps without a gate (refresh), flush or measurement in between are fused
+// into one launch of k_decide_wb (the walkers are independent; only those events need all walkers in step).
 int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_pick) {
     const DevState &S = h->S;
     const int64_t period = h->refresh_every > 0 ? h->refresh_every : S.n_occ;
     const int pgrid = grid_for_warps(S.nw);
-    for (int64_t s = 0; s < n; s++) {
+    const bool delayed = h->update_variant >= 1;
+    const bool woodbury = h->update_variant == 2;
+    for (int64_t s = 0; s < n;) {
         const bool gate = (h->sweeps % period) == 0;            // src/MonteCarlo.jl:595 (pre-increment)
-        const bool delayed = h->update_variant >= 1;
-        const bool woodbury = h->update_variant == 2;
+        int64_t g = 1;
+        if (woodbury && !gate && h->fuse_sweeps) {
+            g = std::min<int64_t>(n - s, KDSL_FLUSH_EVERY - h->since_flush);      // up to the next flush
+            g = std::min<int64_t>(g, period - (h->sweeps % period));               // ... the next gate sweep
+            g = std::min<int64_t>(g, S.n_occ - (h->sweeps % S.n_occ));             // ... the next measurement
+            if (g < 1) g = 1;
+        }
         {
             Span sp(h, KDSL_T_PROPOSE);
             const size_t off = (size_t)s * S.nw;
             if (woodbury) {
                 if (replay)
-                    k_decide_wb<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
+                    k_decide_wb<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, (int)g, h->rp_r + off, h->rp_bond + off,
                                                                     have_pick ? h->rp_pick + off : nullptr);
                 else
-                    k_decide_wb<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, nullptr, nullptr, nullptr);
+                    k_decide_wb<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, (int)g, nullptr, nullptr, nullptr);
                 CK(cudaGetLastError());
             } else if (delayed) {
                 if (replay)
@@ -380,12 +389,14 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             if (rc) return rc;
             h->parity ^= 1;
         }
-        if (delayed && ++h->since_flush >= KDSL_FLUSH_EVERY) {
+        h->since_flush += (int)g;
+        if (delayed && h->since_flush >= KDSL_FLUSH_EVERY) {
             int rc = launch_flush(h, false);
             if (rc) return rc;
         }
-        h->sweeps += 1;                                          // Carlo: ctx.sweeps += 1
-        h->walker_sweeps += S.nw;
+        h->sweeps += g;                                          // Carlo: ctx.sweeps += 1
+        h->walker_sweeps += g * S.nw;
+        s += g;
         if (therm >= 0 && h->sweeps > therm && (h->sweeps % S.n_occ) == 0) {   // :630 (post-increment)
             Span sp(h, KDSL_T_MEASURE);
             if (woodbury) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, nullptr, 1);
@@ -953,6 +964,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         if (value < 1 || value > 4096) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_cols_per_item out of range");
         h->update_ch = (int)value;
     } else if (n == "inverse_variant") h->inverse_variant = (int)value;
+    else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;
     else if (n == "gemm_variant") h->gemm_variant = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);

@@ -104,22 +104,15 @@ __device__ __forceinline__ void wb_accept_warp(const DevState &S, const WbView &
 }
 
 // Carlo.sweep! proposal (reference src/MonteCarlo.jl:538-607), one warp per walker, Woodbury-form W.
+// One sweep of one walker (whole warp).  The Xoshiro state g lives in registers across the sweeps of a launch.
 template <bool REPLAY>
-__global__ void __launch_bounds__(256, 4)
-k_decide_wb(DevState S, int gate_refresh, const double *__restrict__ rp_r, const int *__restrict__ rp_bond,
-            const int *__restrict__ rp_pick) {
-    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (w >= S.nw) return;
+__device__ __forceinline__ void decide_sweep_wb(const DevState &S, int w, int lane, int gate_refresh, Xoshiro &g,
+                                                const double *__restrict__ rp_r, const int *__restrict__ rp_bond,
+                                                const int *__restrict__ rp_pick) {
     const int ns = S.ns;
     int *kup = S.kup + (size_t)w * ns;
     int *kdn = S.kdn + (size_t)w * ns;
     const int zmu = S.zmu[w];
-    Xoshiro g;
-    if (!REPLAY) {
-        const unsigned long long *st = S.rng + (size_t)w * 4;
-        g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
-    }
     const double r = REPLAY ? rp_r[w] : g.rand_f64();               // :546
     const double zr = (double)zmu / (double)S.n_bonds;
     bool accepted = false, reached = false;
@@ -201,18 +194,40 @@ k_decide_wb(DevState S, int gate_refresh, const double *__restrict__ rp_r, const
             S.n_acc[w] += 1ull;
         }
     }
-    if (lane == 0) {
-        if (reached) {
-            S.n_reach[w] += 1ull;
-            if (gate_refresh) {                                     // :595
-                const int slot = atomicAdd(&S.cnt[2], 1);
-                S.ref_list[slot] = w;
-            }
+    if (lane == 0 && reached) {
+        S.n_reach[w] += 1ull;
+        if (gate_refresh) {                                         // :595
+            const int slot = atomicAdd(&S.cnt[2], 1);
+            S.ref_list[slot] = w;
         }
-        if (!REPLAY) {
-            unsigned long long *st = S.rng + (size_t)w * 4;
-            st[0] = g.s0; st[1] = g.s1; st[2] = g.s2; st[3] = g.s3;
-        }
+    }
+}
+
+// Carlo.sweep! for every walker, n_sweeps consecutive proposals per launch (the walkers are independent between
+// two flushes, so the lock-step loop only has to come back to the host at gate / flush / measurement sweeps).
+// Replay inputs of sweep s are at rp_*[s * nw + w].  gate_refresh must be 0 when n_sweeps > 1.
+template <bool REPLAY>
+__global__ void __launch_bounds__(256, 4)
+k_decide_wb(DevState S, int gate_refresh, int n_sweeps, const double *__restrict__ rp_r,
+            const int *__restrict__ rp_bond, const int *__restrict__ rp_pick) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= S.nw) return;
+    Xoshiro g;
+    g.s0 = g.s1 = g.s2 = g.s3 = 0ull;
+    if (!REPLAY) {
+        const unsigned long long *st = S.rng + (size_t)w * 4;
+        g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
+    }
+    for (int s = 0; s < n_sweeps; s++) {
+        const size_t off = (size_t)s * S.nw;
+        decide_sweep_wb<REPLAY>(S, w, lane, gate_refresh, g, REPLAY ? rp_r + off : nullptr,
+                                REPLAY ? rp_bond + off : nullptr, (REPLAY && rp_pick) ? rp_pick + off : nullptr);
+        __syncwarp();                                               // lane-0 / row-owner writes -> next sweep's reads
+    }
+    if (!REPLAY && lane == 0) {
+        unsigned long long *st = S.rng + (size_t)w * 4;
+        st[0] = g.s0; st[1] = g.s1; st[2] = g.s2; st[3] = g.s3;
     }
 }
 
