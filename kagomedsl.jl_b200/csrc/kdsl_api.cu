@@ -24,7 +24,7 @@
 
 #define KDSL_VERSION_NUM 110
 #define KDSL_KTH 16          /* pending factors that trigger a flush */
-#define KDSL_FLUSH_EVERY 4   /* sweeps between flush launches    */
+#define KDSL_FLUSH_EVERY 8   /* sweeps between flush launches    */
 #define KDSL_KMAX (KDSL_KTH + KDSL_FLUSH_EVERY)
 
 static thread_local std::string g_err;
@@ -80,6 +80,8 @@ struct kdsl_handle_s {
     int64_t refresh_every = 0;
     int update_variant = 2, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
     int since_flush = 0;
+    int flush_variant = 0;        // 0: k_flush_wb (persistent, 128-bit), 1: k_flush
+    int flush_every = KDSL_FLUSH_EVERY;   // sweeps between flush launches (kmax = kth + flush_every <= 32)
     int fuse_sweeps = 1;          // fuse consecutive proposals into one launch where the loop allows it
     int inverse_tuning = 0;
     int update_ch = 8;
@@ -289,6 +291,27 @@ int launch_refresh(kdsl_handle h, const int *list) {
     return KDSL_OK;
 }
 
+template <int KPAD>
+int launch_flush_wb_kernel(kdsl_handle h, const int *list, int *cptr) {
+    const DevState &S = h->S;
+    const int Nmax = std::max(S.n_up, S.n_dn);
+    const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KPAD * sizeof(double);
+    {
+        Span sp(h, KDSL_T_UPDATE_PREPARE);
+        k_flush_prepare_dmma<KPAD><<<h->num_sms * 4, 288, 0, h->stream>>>(S, list, cptr, S.nw);
+        CK(cudaGetLastError());
+    }
+    CK(cudaFuncSetAttribute(k_flush_wb<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        Span sp(h, KDSL_T_UPDATE);
+        k_flush_wb<KPAD><<<h->num_sms * 2, 288, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
+        CK(cudaGetLastError());
+    }
+    k_flush_finish_wb<<<1, 1024, 0, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
 // W0 += pending factors for the listed walkers (list = device list with count cnt[4]) or for all walkers
 int launch_flush(kdsl_handle h, bool all) {
     const DevState &S = h->S;
@@ -301,17 +324,27 @@ int launch_flush(kdsl_handle h, bool all) {
         CK(cudaFuncSetAttribute(k_measure_wb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
+    const int *list = all ? nullptr : S.flush_list;
+    int *cptr = all ? nullptr : S.cnt + 4;
+    if (h->update_variant == 2 && h->flush_variant == 0) {
+        int rc = S.kmax <= 20 ? launch_flush_wb_kernel<20>(h, list, cptr)
+               : S.kmax <= 24 ? launch_flush_wb_kernel<24>(h, list, cptr)
+                              : launch_flush_wb_kernel<32>(h, list, cptr);
+        if (rc) return rc;
+        h->since_flush = 0;
+        return KDSL_OK;
+    }
     {
         Span sp(h, KDSL_T_UPDATE);
-        const int *list = all ? nullptr : S.flush_list;
-        int *cptr = all ? nullptr : S.cnt + 4;
         if (h->update_variant == 2) {
+            if (S.kmax != KDSL_KMAX) return fail(KDSL_ERR_STATE, "flush_variant 1 needs kmax = %d", KDSL_KMAX);
             const size_t psm = (size_t)S.kmax * S.kmax * sizeof(double) + 2 * S.kmax * sizeof(int);
             k_flush_prepare<<<h->num_sms * 4, 256, psm, h->stream>>>(S, list, cptr, S.nw);
             CK(cudaGetLastError());
+            k_flush<KDSL_KMAX, true><<<h->num_sms * 4, 288, smem, h->stream>>>(S, list, cptr, S.nw);
+        } else {
+            k_flush<KDSL_KMAX, false><<<h->num_sms * 4, 288, smem, h->stream>>>(S, list, cptr, S.nw);
         }
-        if (h->update_variant == 2) k_flush<KDSL_KMAX, true><<<h->num_sms * 4, 288, smem, h->stream>>>(S, list, cptr, S.nw);
-        else k_flush<KDSL_KMAX, false><<<h->num_sms * 4, 288, smem, h->stream>>>(S, list, cptr, S.nw);
         CK(cudaGetLastError());
         k_flush_done<<<8, 256, 0, h->stream>>>(S, list, cptr, S.nw);
         CK(cudaGetLastError());
@@ -346,7 +379,7 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
         const bool gate = (h->sweeps % period) == 0;            // src/MonteCarlo.jl:595 (pre-increment)
         int64_t g = 1;
         if (woodbury && !gate && h->fuse_sweeps) {
-            g = std::min<int64_t>(n - s, KDSL_FLUSH_EVERY - h->since_flush);      // up to the next flush
+            g = std::min<int64_t>(n - s, h->flush_every - h->since_flush);      // up to the next flush
             g = std::min<int64_t>(g, period - (h->sweeps % period));               // ... the next gate sweep
             g = std::min<int64_t>(g, S.n_occ - (h->sweeps % S.n_occ));             // ... the next measurement
             if (g < 1) g = 1;
@@ -390,7 +423,7 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             h->parity ^= 1;
         }
         h->since_flush += (int)g;
-        if (delayed && h->since_flush >= KDSL_FLUSH_EVERY) {
+        if (delayed && h->since_flush >= h->flush_every) {
             int rc = launch_flush(h, false);
             if (rc) return rc;
         }
@@ -559,11 +592,11 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     ALLOC(S.acc_list, 12 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
     ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
     ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 4);
-    S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;
-    ALLOC(S.facA_up, nw * S.kmax * ns); ALLOC(S.facA_dn, nw * S.kmax * ns);
-    ALLOC(S.facB_up, nw * S.kmax * n_up); ALLOC(S.facB_dn, nw * S.kmax * n_dn);
+    S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;                  // (the buffers are sized for the largest kmax = 32)
+    ALLOC(S.facA_up, nw * KDSL_KALLOC * ns); ALLOC(S.facA_dn, nw * KDSL_KALLOC * ns);
+    ALLOC(S.facB_up, nw * KDSL_KALLOC * ((n_up + 7) / 8 * 8)); ALLOC(S.facB_dn, nw * KDSL_KALLOC * ((n_dn + 7) / 8 * 8));
     ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw);
-    ALLOC(S.wbT, 2 * nw * S.kmax * S.kmax); ALLOC(S.wbK, 2 * nw * S.kmax); ALLOC(S.wbL, 2 * nw * S.kmax);
+    ALLOC(S.wbT, 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
     h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
     ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
@@ -958,6 +991,10 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         }
         h->parity = 0;
         h->update_variant = (int)value;
+        if (h->have_config) CK(cudaStreamSynchronize(h->stream));
+        h->flush_every = KDSL_FLUSH_EVERY;                // the factor-list kernels are compiled for kmax = 20
+        h->S.kth = KDSL_KTH;
+        h->S.kmax = KDSL_KMAX;
     }
     else if (n == "update_ctas_per_sm") h->update_ctas_per_sm = (int)value;
     else if (n == "update_cols_per_item") {
@@ -965,6 +1002,26 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         h->update_ch = (int)value;
     } else if (n == "inverse_variant") h->inverse_variant = (int)value;
     else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;
+    else if (n == "flush_variant") h->flush_variant = (int)value;
+    else if (n == "flush_every" || n == "flush_threshold") {
+        // Woodbury mode only: a walker is flushed at the first flush launch after it reached `flush_threshold`
+        // pending updates; launches come every `flush_every` sweeps, so at most threshold + every are ever pending
+        if (h->update_variant != 2) return fail(KDSL_ERR_STATE, "%s applies to update_variant 2 only", name);
+        const int fe = n == "flush_every" ? (int)value : h->flush_every;
+        const int kth = n == "flush_threshold" ? (int)value : h->S.kth;
+        if (fe < 1 || kth < 1 || fe + kth > KDSL_KALLOC)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "need flush_every >= 1, flush_threshold >= 1 and their sum <= %d", KDSL_KALLOC);
+        int rc = use_device(h);
+        if (rc) return rc;
+        if (h->have_config && h->W_valid) {               // strides change: no update may be pending
+            rc = launch_flush(h, true);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        h->flush_every = fe;
+        h->S.kth = kth;
+        h->S.kmax = fe + kth;
+    }
     else if (n == "gemm_variant") h->gemm_variant = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #define KDSL_WARP 32
+#define KDSL_KALLOC 32        /* capacity of the pending-update buffers (warp-wide Woodbury state) */
 
 // Device view of one engine (passed by value to every kernel).
 // Layout in HBM (nw = walkers on this GPU, all arrays walker-major):

@@ -12,6 +12,7 @@
 #pragma once
 #include "kdsl_common.cuh"
 #include "kdsl_propose.cuh"
+#include "kdsl_refresh_fast.cuh"
 
 struct WbView {
     const double *W0;
@@ -272,6 +273,162 @@ k_flush_prepare(DevState S, const int *__restrict__ list, const int *__restrict_
         __syncthreads();
         double *B = (spin ? S.facB_dn : S.facB_up) + (size_t)w * kmax * v.N;
         wb_compute_G_cta(v, sT, sK, sL, B, v.N, -1.0, tid, blockDim.x);
+    }
+}
+
+// DMMA version of k_flush_prepare for k_flush_wb: G = -T Rt (KPAD x N, zero padded) per (list entry, species),
+// written in the fragment-major order k_flush_wb consumes (element (column j, factor m) at frag_idx(j, m, KPAD)),
+// so that its staging is a linear copy.  Rt is gathered from W0 directly in fragment order (no redundant reads).
+// One CTA of 288 threads per item; warp = group of column tiles.
+template <int KPAD>
+__global__ void __launch_bounds__(288)
+k_flush_prepare_dmma(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed) {
+    constexpr int KS = KPAD / 4, MT = (KPAD + 7) / 8;
+    __shared__ double sT[MT * 8 * KPAD];                  // T, frag-major (r = m, k = n), zero padded
+    __shared__ int sK[KPAD], sL[KPAD];
+    const int count = count_ptr ? *count_ptr : count_fixed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gr = lane >> 2, tg = lane & 3;
+    for (int item = blockIdx.x; item < 2 * count; item += gridDim.x) {
+        const int e = item >> 1, spin = item & 1;
+        const int w = list ? list[e] : e;
+        const WbView v = wb_view(S, w, spin);
+        const int k = v.k, kmax = S.kmax, ns = v.ns, N = v.N;
+        if (k == 0) continue;
+        __syncthreads();
+        for (int x = tid; x < MT * 8 * KPAD; x += 288) {
+            const int m = x / KPAD, n = x - m * KPAD;
+            sT[frag_idx(m, n, KPAD)] = (m < k && n < k) ? v.T[m * kmax + n] : 0.0;
+        }
+        if (tid < KPAD) { sK[tid] = tid < k ? v.Ks[tid] : 0; sL[tid] = tid < k ? v.Ls[tid] : -1; }
+        __syncthreads();
+        const int ctiles = (N + 7) >> 3;
+        double *G = (spin ? S.facB_dn : S.facB_up) + (size_t)w * KDSL_KALLOC * (ctiles << 3);
+        for (int ct = warp; ct < ctiles; ct += 9) {
+            const int j = (ct << 3) + gr;
+            double rt[KS];                                // B operand (k = n, col = j): Rt[n][j]
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                const int n = 4 * q + tg;
+                rt[q] = (n < k && j < N) ? v.W0[(size_t)j * ns + sK[n]] - (sL[n] == j ? 1.0 : 0.0) : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < MT; t++) {
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < KS; q++) dmma_8x8x4(d0, d1, sT[(((t * KS) + q) << 5) + lane], rt[q]);
+                // D[m = 8t + gr][j = 8 ct + 2 tg + e]  ->  frag_idx(j, m, KPAD)
+                const int m = 8 * t + gr;
+                if (m < KPAD) {
+                    double *dst = G + ((((size_t)ct * KS) + (m >> 2)) << 5) + (m & 3);
+                    dst[(2 * tg) << 2] = -d0;
+                    dst[(2 * tg + 1) << 2] = -d1;
+                }
+            }
+        }
+    }
+}
+
+// W0 += C G for the listed walkers (C = columns l_m of W0 itself, G = facB from k_flush_prepare_dmma): the HBM-bound pass
+// of the delayed update, Woodbury form.  Persistent CTAs (two per SM) fetch work items from a device counter;
+// item = (list entry, species, block of 216 rows); 9 warps, each owns a strip of 24 rows and walks over all
+// column tiles with the DMMA in transposed form (D[column][row]: every lane moves two adjacent rows of one column,
+// i.e. 128-bit loads / stores, 64 contiguous bytes per column and warp) and three tiles of loads in flight.
+template <int KPAD>
+__global__ void __launch_bounds__(288, 2)
+k_flush_wb(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
+           int *__restrict__ work_counter) {
+    constexpr int KS = KPAD / 4, RT = 3;
+    extern __shared__ double fsm[];                      // G, frag-major (r = column j, k = m)
+    __shared__ int s_item;
+    const int count = count_ptr ? *count_ptr : count_fixed;
+    const int ns = S.ns;
+    const int nrb = (ns + 215) / 216;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gr = lane >> 2, tg = lane & 3;
+    const int total = count * 2 * nrb;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int e = item / (2 * nrb);
+        const int rem = item - e * 2 * nrb;
+        const int spin = rem / nrb, rb = rem - spin * nrb;
+        const int w = list ? list[e] : e;
+        const int cnt = S.fcnt[2 * w + spin];
+        if (cnt == 0) continue;                           // uniform over the block
+        const int N = spin ? S.n_dn : S.n_up;
+        const int ctiles = (N + 7) >> 3;
+        const double *B = (spin ? S.facB_dn : S.facB_up) + (size_t)w * KDSL_KALLOC * (ctiles << 3);
+        const int *Ls = S.wbL + ((size_t)w * 2 + spin) * S.kmax;
+        double *W0 = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
+        for (int x = tid; x < ctiles * 8 * KPAD; x += 288) fsm[x] = B[x];       // already fragment-major and zero padded
+        const int r0 = rb * 216 + warp * 24;
+        double af[RT][KS];                                // C^T fragments (k = m, n = row): W0[row, l_m]
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int m = 4 * s + tg;
+            const int lm = m < cnt ? Ls[m] : 0;
+#pragma unroll
+            for (int t = 0; t < RT; t++) {
+                const int row = r0 + 8 * t + gr;
+                af[t][s] = (row < ns && m < cnt) ? W0[(size_t)lm * ns + row] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (r0 >= ns) continue;
+        bool rv[RT];
+#pragma unroll
+        for (int t = 0; t < RT; t++) rv[t] = r0 + 8 * t + 2 * tg < ns;     // ns is even: both rows or none
+        double2 *base = reinterpret_cast<double2 *>(W0 + (size_t)gr * ns + r0 + 2 * tg);
+        const size_t cstride = (size_t)4 * ns;            // 8 columns, in double2 units
+        auto load_tile = [&](int ct, double2 (&cc)[RT]) {
+            const bool cok = (ct << 3) + gr < N;
+#pragma unroll
+            for (int t = 0; t < RT; t++)
+                cc[t] = (rv[t] && cok) ? base[(size_t)ct * cstride + 4 * t] : make_double2(0.0, 0.0);
+        };
+        auto compute_store = [&](int ct, double2 (&cc)[RT]) {
+#pragma unroll
+            for (int s = 0; s < KS; s++) {
+                const double gf = fsm[(((ct * KS) + s) << 5) + lane];
+#pragma unroll
+                for (int t = 0; t < RT; t++) dmma_8x8x4(cc[t].x, cc[t].y, gf, af[t][s]);
+            }
+            const bool cok = (ct << 3) + gr < N;
+#pragma unroll
+            for (int t = 0; t < RT; t++)
+                if (rv[t] && cok) base[(size_t)ct * cstride + 4 * t] = cc[t];
+        };
+        double2 c0[RT], c1[RT], c2[RT];
+        load_tile(0, c0);
+        if (1 < ctiles) load_tile(1, c1);
+        for (int ct = 0; ct < ctiles; ct += 3) {           // three-deep register pipeline
+            if (ct + 2 < ctiles) load_tile(ct + 2, c2);
+            compute_store(ct, c0);
+            if (ct + 3 < ctiles) load_tile(ct + 3, c0);
+            if (ct + 1 < ctiles) compute_store(ct + 1, c1);
+            if (ct + 4 < ctiles) load_tile(ct + 4, c1);
+            if (ct + 2 < ctiles) compute_store(ct + 2, c2);
+        }
+    }
+}
+
+// after k_flush_wb (one CTA): the listed walkers have no pending updates; re-arm the list and the work counter
+__global__ void __launch_bounds__(1024)
+k_flush_finish_wb(DevState S, const int *__restrict__ list, int *count_ptr, int count_fixed, int *work_counter) {
+    const int count = count_ptr ? *count_ptr : count_fixed;
+    for (int e = threadIdx.x; e < count; e += blockDim.x) {
+        const int w = list ? list[e] : e;
+        S.fcnt[(size_t)2 * w] = 0;
+        S.fcnt[(size_t)2 * w + 1] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (count_ptr) { S.upd_moves[1] += (unsigned long long)count; *count_ptr = 0; }
+        *work_counter = 0;
     }
 }
 
