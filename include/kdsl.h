@@ -64,8 +64,7 @@ typedef struct kdsl_handle_s *kdsl_handle;
 #define KDSL_T_REFRESH_INVERSE 3
 #define KDSL_T_REFRESH_GEMM 4
 #define KDSL_T_MEASURE 5
-#define KDSL_T_UPDATE_PREPARE 6 /* delayed updates: right factor G = -T Rt of the walkers about to be flushed */
-#define KDSL_N_TIMERS 7
+#define KDSL_N_TIMERS 6
 
 int kdsl_version(void);
 /* thread-local message of the last failing call on this thread */

@@ -22,7 +22,7 @@ FLAG_SINGULAR, FLAG_NONFINITE, FLAG_BAD_SITE = 1, 2, 4
 (ACC_WALKER_SWEEPS, ACC_SUM_ACC, ACC_SUM_OL, ACC_SUM_OL2, ACC_N_OL, ACC_N_REACH, ACC_N_REFRESH,
  ACC_N_SINGULAR) = range(8)
 N_ACC = 8
-TIMER_NAMES = ("propose", "update", "refresh_gather", "refresh_inverse", "refresh_gemm", "measure", "update_prepare")
+TIMER_NAMES = ("propose", "update", "refresh_gather", "refresh_inverse", "refresh_gemm", "measure")
 N_TIMERS = len(TIMER_NAMES)
 
 # every symbol include/kdsl.h declares (tests check the library exports exactly these)

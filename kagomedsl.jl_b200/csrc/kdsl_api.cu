@@ -296,11 +296,6 @@ int launch_flush_wb_kernel(kdsl_handle h, const int *list, int *cptr) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
     const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KPAD * sizeof(double);
-    {
-        Span sp(h, KDSL_T_UPDATE_PREPARE);
-        k_flush_prepare_dmma<KPAD><<<h->num_sms * 4, 288, 0, h->stream>>>(S, list, cptr, S.nw);
-        CK(cudaGetLastError());
-    }
     CK(cudaFuncSetAttribute(k_flush_wb<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Span sp(h, KDSL_T_UPDATE);

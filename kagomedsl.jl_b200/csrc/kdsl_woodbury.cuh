@@ -16,6 +16,7 @@
 
 struct WbView {
     const double *W0;
+    double *rows;    // [kmax][N] raw rows W0[K_n, :] of the displaced particles' new sites (filled on accept)
     double *T;       // [kmax][kmax] row-major
     int *Ks, *Ls;    // [kmax] target sites / labels (0-based)
     int ns, N, k;
@@ -27,6 +28,7 @@ __device__ __forceinline__ WbView wb_view(const DevState &S, int w, int spin) {
     v.N = spin ? S.n_dn : S.n_up;
     v.W0 = (spin ? S.W_dn : S.W_up) + (size_t)w * S.ns * v.N;
     const size_t q = (size_t)w * 2 + spin;
+    v.rows = (spin ? S.facA_dn : S.facA_up) + (size_t)w * KDSL_KALLOC * S.ns;
     v.T = S.wbT + q * S.kmax * S.kmax;
     v.Ks = S.wbK + q * S.kmax;
     v.Ls = S.wbL + q * S.kmax;
@@ -63,9 +65,39 @@ __device__ __forceinline__ WbEval wb_entry_warp(const DevState &S, const WbView 
     return e;
 }
 
+// rows[slot][:] = W0[K_slot, :] for the slots in the two masks (one strided gather per displaced particle, done once
+// at the end of a launch).  One slot of each species per round, all loads of a round issued before its stores (the
+// pointers may alias as far as the compiler knows), so a round costs one memory latency.
+__device__ __forceinline__ void wb_copy_rows(const DevState &S, int w, unsigned mask_up, unsigned mask_dn, int lane) {
+    const WbView vu = wb_view(S, w, 0), vd = wb_view(S, w, 1);
+    while (mask_up | mask_dn) {
+        const int su = mask_up ? __ffs(mask_up) - 1 : -1, sd = mask_dn ? __ffs(mask_dn) - 1 : -1;
+        mask_up &= mask_up - 1u;
+        mask_dn &= mask_dn - 1u;
+        const int Ku = su >= 0 ? vu.Ks[su] : 0, Kd = sd >= 0 ? vd.Ks[sd] : 0;
+        const int Nmax = max(vu.N, vd.N);
+        for (int c0 = 0; c0 < Nmax; c0 += 128) {
+            double tu[4], td[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = c0 + 32 * q + lane;
+                tu[q] = (su >= 0 && c < vu.N) ? vu.W0[(size_t)c * vu.ns + Ku] : 0.0;
+                td[q] = (sd >= 0 && c < vd.N) ? vd.W0[(size_t)c * vd.ns + Kd] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = c0 + 32 * q + lane;
+                if (su >= 0 && c < vu.N) vu.rows[(size_t)su * vu.N + c] = tu[q];
+                if (sd >= 0 && c < vd.N) vd.rows[(size_t)sd * vd.N + c] = td[q];
+            }
+        }
+    }
+}
+
 // Apply the accepted move "label l -> site K" to the Woodbury state of one species (whole warp).
-__device__ __forceinline__ void wb_accept_warp(const DevState &S, const WbView &v, const WbEval &e, int w,
-                                               int spin, int K, int l, int lane) {
+// Returns the slot of the displaced-particle list that now refers to site K (its row copy is refreshed by the caller).
+__device__ __forceinline__ int wb_accept_warp(const DevState &S, const WbView &v, const WbEval &e, int w,
+                                              int spin, int K, int l, int lane) {
     const int k = v.k, kmax = S.kmax;
     double y = 0.0;                                                          // (c^T T)_n on lane n
     for (int m = 0; m < k; m++) {
@@ -89,6 +121,7 @@ __device__ __forceinline__ void wb_accept_warp(const DevState &S, const WbView &
             v.Ls[k] = l;
             S.fcnt[(size_t)w * 2 + spin] = k + 1;
         }
+        return k;
     } else {
         // label already displaced: row j of S becomes W0[K, L] = c.  T' = T - (T e_j) w^T / (c^T T)_j, w = c^T T - e_j
         const int j = e.j;
@@ -101,6 +134,7 @@ __device__ __forceinline__ void wb_accept_warp(const DevState &S, const WbView &
             if (lane < k) v.T[lane * kmax + n] = fma(-tj, wn, v.T[lane * kmax + n]);
         }
         if (lane == 0) v.Ks[j] = K;
+        return j;
     }
 }
 
@@ -109,7 +143,7 @@ __device__ __forceinline__ void wb_accept_warp(const DevState &S, const WbView &
 template <bool REPLAY>
 __device__ __forceinline__ void decide_sweep_wb(const DevState &S, int w, int lane, int gate_refresh, Xoshiro &g,
                                                 const double *__restrict__ rp_r, const int *__restrict__ rp_bond,
-                                                const int *__restrict__ rp_pick) {
+                                                const int *__restrict__ rp_pick, unsigned &dirty_up, unsigned &dirty_dn) {
     const int ns = S.ns;
     int *kup = S.kup + (size_t)w * ns;
     int *kdn = S.kdn + (size_t)w * ns;
@@ -156,8 +190,8 @@ __device__ __forceinline__ void decide_sweep_wb(const DevState &S, int w, int la
     }
     if (accepted) {
         if (!gate_refresh) {                                        // (a walker re-evaluated this sweep needs no update)
-            wb_accept_warp(S, vu, eu, w, 0, K_up, l_up - 1, lane);
-            wb_accept_warp(S, vd, ed, w, 1, K_dn, l_dn - 1, lane);
+            dirty_up |= 1u << wb_accept_warp(S, vu, eu, w, 0, K_up, l_up - 1, lane);
+            dirty_dn |= 1u << wb_accept_warp(S, vd, ed, w, 1, K_dn, l_dn - 1, lane);
             const int knew = max(vu.k + (eu.j < 0), vd.k + (ed.j < 0)), kold = max(vu.k, vd.k);
             if (lane == 0 && knew == S.kth && kold < S.kth) {       // due for a flush (listed exactly once)
                 const int fs = atomicAdd(&S.cnt[4], 1);
@@ -220,12 +254,15 @@ k_decide_wb(DevState S, int gate_refresh, int n_sweeps, const double *__restrict
         const unsigned long long *st = S.rng + (size_t)w * 4;
         g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
     }
+    unsigned dirty_up = 0u, dirty_dn = 0u;                          // displaced-particle slots (re)assigned in this launch
     for (int s = 0; s < n_sweeps; s++) {
         const size_t off = (size_t)s * S.nw;
         decide_sweep_wb<REPLAY>(S, w, lane, gate_refresh, g, REPLAY ? rp_r + off : nullptr,
-                                REPLAY ? rp_bond + off : nullptr, (REPLAY && rp_pick) ? rp_pick + off : nullptr);
+                                REPLAY ? rp_bond + off : nullptr, (REPLAY && rp_pick) ? rp_pick + off : nullptr,
+                                dirty_up, dirty_dn);
         __syncwarp();                                               // lane-0 / row-owner writes -> next sweep's reads
     }
+    wb_copy_rows(S, w, dirty_up, dirty_dn, lane);                   // raw rows W0[K, :] for the next flush
     if (!REPLAY && lane == 0) {
         unsigned long long *st = S.rng + (size_t)w * 4;
         st[0] = g.s0; st[1] = g.s1; st[2] = g.s2; st[3] = g.s3;
@@ -276,60 +313,7 @@ k_flush_prepare(DevState S, const int *__restrict__ list, const int *__restrict_
     }
 }
 
-// DMMA version of k_flush_prepare for k_flush_wb: G = -T Rt (KPAD x N, zero padded) per (list entry, species),
-// written in the fragment-major order k_flush_wb consumes (element (column j, factor m) at frag_idx(j, m, KPAD)),
-// so that its staging is a linear copy.  Rt is gathered from W0 directly in fragment order (no redundant reads).
-// One CTA of 288 threads per item; warp = group of column tiles.
-template <int KPAD>
-__global__ void __launch_bounds__(288)
-k_flush_prepare_dmma(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed) {
-    constexpr int KS = KPAD / 4, MT = (KPAD + 7) / 8;
-    __shared__ double sT[MT * 8 * KPAD];                  // T, frag-major (r = m, k = n), zero padded
-    __shared__ int sK[KPAD], sL[KPAD];
-    const int count = count_ptr ? *count_ptr : count_fixed;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gr = lane >> 2, tg = lane & 3;
-    for (int item = blockIdx.x; item < 2 * count; item += gridDim.x) {
-        const int e = item >> 1, spin = item & 1;
-        const int w = list ? list[e] : e;
-        const WbView v = wb_view(S, w, spin);
-        const int k = v.k, kmax = S.kmax, ns = v.ns, N = v.N;
-        if (k == 0) continue;
-        __syncthreads();
-        for (int x = tid; x < MT * 8 * KPAD; x += 288) {
-            const int m = x / KPAD, n = x - m * KPAD;
-            sT[frag_idx(m, n, KPAD)] = (m < k && n < k) ? v.T[m * kmax + n] : 0.0;
-        }
-        if (tid < KPAD) { sK[tid] = tid < k ? v.Ks[tid] : 0; sL[tid] = tid < k ? v.Ls[tid] : -1; }
-        __syncthreads();
-        const int ctiles = (N + 7) >> 3;
-        double *G = (spin ? S.facB_dn : S.facB_up) + (size_t)w * KDSL_KALLOC * (ctiles << 3);
-        for (int ct = warp; ct < ctiles; ct += 9) {
-            const int j = (ct << 3) + gr;
-            double rt[KS];                                // B operand (k = n, col = j): Rt[n][j]
-#pragma unroll
-            for (int q = 0; q < KS; q++) {
-                const int n = 4 * q + tg;
-                rt[q] = (n < k && j < N) ? v.W0[(size_t)j * ns + sK[n]] - (sL[n] == j ? 1.0 : 0.0) : 0.0;
-            }
-#pragma unroll
-            for (int t = 0; t < MT; t++) {
-                double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int q = 0; q < KS; q++) dmma_8x8x4(d0, d1, sT[(((t * KS) + q) << 5) + lane], rt[q]);
-                // D[m = 8t + gr][j = 8 ct + 2 tg + e]  ->  frag_idx(j, m, KPAD)
-                const int m = 8 * t + gr;
-                if (m < KPAD) {
-                    double *dst = G + ((((size_t)ct * KS) + (m >> 2)) << 5) + (m & 3);
-                    dst[(2 * tg) << 2] = -d0;
-                    dst[(2 * tg + 1) << 2] = -d1;
-                }
-            }
-        }
-    }
-}
-
-// W0 += C G for the listed walkers (C = columns l_m of W0 itself, G = facB from k_flush_prepare_dmma): the HBM-bound pass
+// W0 += C G for the listed walkers (C = columns l_m of W0 itself, G = -T Rt built in the kernel): the HBM-bound pass
 // of the delayed update, Woodbury form.  Persistent CTAs (two per SM) fetch work items from a device counter;
 // item = (list entry, species, block of 216 rows); 9 warps, each owns a strip of 24 rows and walks over all
 // column tiles with the DMMA in transposed form (D[column][row]: every lane moves two adjacent rows of one column,
@@ -338,8 +322,10 @@ template <int KPAD>
 __global__ void __launch_bounds__(288, 2)
 k_flush_wb(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
            int *__restrict__ work_counter) {
-    constexpr int KS = KPAD / 4, RT = 3;
+    constexpr int KS = KPAD / 4, RT = 3, MT = (KPAD + 7) / 8;
     extern __shared__ double fsm[];                      // G, frag-major (r = column j, k = m)
+    __shared__ double sT[MT * 8 * KPAD];                 // T, frag-major (r = m, k = n), zero padded
+    __shared__ int sL[KPAD];
     __shared__ int s_item;
     const int count = count_ptr ? *count_ptr : count_fixed;
     const int ns = S.ns;
@@ -361,10 +347,38 @@ k_flush_wb(DevState S, const int *__restrict__ list, const int *__restrict__ cou
         if (cnt == 0) continue;                           // uniform over the block
         const int N = spin ? S.n_dn : S.n_up;
         const int ctiles = (N + 7) >> 3;
-        const double *B = (spin ? S.facB_dn : S.facB_up) + (size_t)w * KDSL_KALLOC * (ctiles << 3);
-        const int *Ls = S.wbL + ((size_t)w * 2 + spin) * S.kmax;
+        const WbView v = wb_view(S, w, spin);
+        const int *Ls = v.Ls;
         double *W0 = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
-        for (int x = tid; x < ctiles * 8 * KPAD; x += 288) fsm[x] = B[x];       // already fragment-major and zero padded
+        // G = -T Rt (KPAD x N) for this walker and species, straight into shared memory in fragment order:
+        // Rt[n][j] = W0[K_n, j] - delta(l_n, j) comes from the row copies made when the moves were accepted
+        for (int x = tid; x < MT * 8 * KPAD; x += 288) {
+            const int m = x / KPAD, n = x - m * KPAD;
+            sT[frag_idx(m, n, KPAD)] = (m < cnt && n < cnt) ? v.T[m * S.kmax + n] : 0.0;
+        }
+        if (tid < KPAD) sL[tid] = tid < cnt ? Ls[tid] : -1;
+        __syncthreads();
+        for (int ct = warp; ct < ctiles; ct += 9) {
+            const int j = (ct << 3) + gr;
+            double rt[KS];                                // B operand (k = n, col = j)
+#pragma unroll
+            for (int q = 0; q < KS; q++) {
+                const int n = 4 * q + tg;
+                rt[q] = (n < cnt && j < N) ? v.rows[(size_t)n * N + j] - (sL[n] == j ? 1.0 : 0.0) : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < MT; t++) {
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < KS; q++) dmma_8x8x4(d0, d1, sT[(((t * KS) + q) << 5) + lane], rt[q]);
+                const int m = 8 * t + gr;                 // D[m][j = 8 ct + 2 tg + e] -> frag_idx(j, m, KPAD)
+                if (m < KPAD) {
+                    double *dst = fsm + ((((size_t)ct * KS) + (m >> 2)) << 5) + (m & 3);
+                    dst[(2 * tg) << 2] = -d0;
+                    dst[(2 * tg + 1) << 2] = -d1;
+                }
+            }
+        }
         const int r0 = rb * 216 + warp * 24;
         double af[RT][KS];                                // C^T fragments (k = m, n = row): W0[row, l_m]
 #pragma unroll
