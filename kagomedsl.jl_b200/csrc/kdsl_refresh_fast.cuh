@@ -410,7 +410,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     double (*sB)[TN * KT] = reinterpret_cast<double (*)[TN * KT]>(gsm + 2 * TM * KT);
     __shared__ int sSrc[TN];
     __shared__ int sRowSite[TM + 1];
-    __shared__ int sKp[1024];                              // contraction index -> column of U (implicit-pivoting inverse)
+    __shared__ int sKp[1024 + 32];                         // contraction index -> column of U (implicit-pivoting inverse)
     const int b = blockIdx.y, spin = blockIdx.z;
     if (b >= batch_count(S, list)) return;
     if (status[2 * b] | status[2 * b + 1]) return;
@@ -431,7 +431,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     const int wm = warp % 3, wn = warp / 3;
     if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
     if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
-    for (int k = tid; k < N; k += NT) sKp[k] = perm_k ? colsrc[k] : k;
+    for (int k = tid; k < 1024 + 32; k += NT) sKp[k] = k < N ? (perm_k ? colsrc[k] : k) : 0;
     __syncthreads();
 
     constexpr int PER = TM * KT / NT;                  // elements of each operand per thread per stage

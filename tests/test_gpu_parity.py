@@ -268,3 +268,85 @@ def test_exact_energy_12_sites(kd):
     err = per_walker.std(ddof=1) / np.sqrt(nw)
     assert abs(mean - (-0.3714938624)) < 5 * err + 1e-5, (mean, err)
     assert err < 5e-4
+
+
+def _run_chain(kd, ham, ku, kdn, states, n_sweeps, options):
+    nw = ku.shape[0]
+    eng = kd.Engine(ham, nw)
+    for k, v in options.items():
+        eng.set_option(k, v)
+    eng.set_config(ku, kdn)
+    eng.set_rng(states)
+    eng.refresh()
+    eng.sweep(n_sweeps, thermalization=0)
+    out = (eng.get_config(), eng.accumulators(per_walker=True), eng.get_rng().copy(),
+           [eng.get_W(w, s) for w in range(nw) for s in (0, 1)], eng.Z())
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("options", [
+    {"fuse_sweeps": 0},
+    {"flush_every": 4},
+    {"flush_every": 3, "flush_threshold": 5},
+    {"flush_every": 16, "flush_threshold": 16},
+    {"flush_variant": 1},
+    {"update_variant": 0},
+])
+def test_launch_grouping_and_flush_cadence_do_not_change_the_chain(kd, options):
+    """Fusing proposals into one launch, the flush cadence and the flush kernel are scheduling choices: configurations,
+    counters, RNG states and O_L sums must be identical to the default path; W agrees to rounding."""
+    lat, ham = U.problem(6, 6)
+    ns, nw, n_sweeps = kd.ns(lat), 24, 700
+    rng = np.random.default_rng(77)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=500.0)
+    states = kd.walker_states(99, nw)
+    ref = _run_chain(kd, ham, ku, kdn, states, n_sweeps, {})
+    got = _run_chain(kd, ham, ku, kdn, states, n_sweeps, options)
+    assert np.array_equal(ref[0][0], got[0][0]) and np.array_equal(ref[0][1], got[0][1])
+    assert np.array_equal(ref[2], got[2])                                   # Xoshiro states
+    assert np.array_equal(ref[1][1], got[1][1])                             # accepted moves per walker
+    assert np.array_equal(ref[4][0], got[4][0]) and np.array_equal(got[4][0], got[4][1])   # Z_mu, incremental == recount
+    assert ref[1][0][kd._lib.ACC_N_REFRESH] == got[1][0][kd._lib.ACC_N_REFRESH]
+    assert np.allclose(ref[1][2], got[1][2], rtol=1e-11, atol=1e-11)         # O_L sums per walker
+    for a, b in zip(ref[3], got[3]):
+        assert U.relerr(a, b) < 1e-11
+    if options == {"fuse_sweeps": 0}:                                        # same arithmetic, different launches: bit-identical
+        for a, b in zip(ref[3], got[3]):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,nw,n_sweeps", [(12, 48, 500), (18, 6, 1000)])
+def test_full_size_invariants(kd, n, nw, n_sweeps):
+    """BASELINE configs 3 and 4 (432 / 972 sites): size-independent properties instead of an oracle replay.
+    W tilde_U = U (the definition of W), unit rows at occupied sites, incremental Z_mu == recount, and after a chain
+    with delayed updates the maintained W equals a from-scratch re-evaluation of the final configuration."""
+    lat, ham = U.problem(n, n)
+    ns = kd.ns(lat)
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ns // 2)
+    ku = np.tile(ku0, (nw, 1)); kdn = np.tile(kd0, (nw, 1))
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.set_rng(kd.walker_states(5, nw))
+    eng.refresh()
+    eng.sweep(n_sweeps, thermalization=0)
+    z, zr = eng.Z()
+    assert np.array_equal(z, zr)
+    gku, gkd = eng.get_config()
+    assert not np.array_equal(gku[0], gku[1])                               # the walkers decorrelated
+    W_run = [(eng.get_W(w, 0), eng.get_W(w, 1)) for w in (0, nw - 1)]
+    ol_run = eng.measure()
+    eng.refresh()
+    ol_ref = eng.measure()
+    assert np.allclose(ol_run, ol_ref, rtol=1e-9, atol=1e-9)
+    for (Wu, Wd), w in zip(W_run, (0, nw - 1)):
+        for spin, (W, U_, kap) in enumerate(((Wu, ham.U_up, gku[w]), (Wd, ham.U_down, gkd[w]))):
+            Wf = eng.get_W(w, spin)
+            assert U.relerr(W, Wf) < 1e-9                                   # rank-1 history vs from scratch
+            Ut = kd.tilde_U(U_, kap)
+            assert np.max(np.abs(Wf @ Ut - U_)) < 1e-10 * max(1.0, np.max(np.abs(Wf)))
+            occ = np.nonzero(kap)[0]
+            E = np.zeros_like(Wf[occ]); E[np.arange(len(occ)), kap[occ] - 1] = 1.0
+            assert np.array_equal(Wf[occ], E)                               # exact unit rows
+    assert eng.accumulators()[kd._lib.ACC_N_SINGULAR] == 0
+    eng.close()
