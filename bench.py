@@ -250,37 +250,47 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"
-    # The HBM-bound W update of the production path: k_flush folds the >= 16 pending rank-1 factors of a walker
-    # into W with ONE read+write pass (delayed Sherman-Morrison).  Algorithmic bytes per launch = walkers
-    # flushed x 16 ns^2; the reference's immediate rank-1 update would move 16 ns^2 per ACCEPTED move.
+    # Rooflines.  (1) The HBM-bound W update of the production path: k_flush_wb folds the >= 16 pending rank-1 updates
+    # of a walker into W with ONE read+write pass (delayed Sherman-Morrison, Woodbury form).  Algorithmic bytes per
+    # launch = walkers flushed x 16 ns^2; the reference's immediate update moves 16 ns^2 per ACCEPTED move.
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     n_flush = upd.get("flushes", 0)
     achieved = n_flush * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else 0.0
     moves_total = res["sum_acc"] / world                 # accepted moves on this rank (all folded by flush or refresh)
-    roofline = {"bound": "hbm", "kernel": "k_flush (delayed rank-k Sherman-Morrison update of W, DMMA)", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "walkers_flushed_per_launch": n_flush / max(upd["launches"], 1), "algorithmic_bytes_per_flush": B_acc,
-                "avg_launch_us": 1e3 * upd["ms"] / max(upd["launches"], 1),
-                "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None,
-                "rank1_equivalent_GBs": moves_total * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
-                "note": "rank1_equivalent = accepted moves x 16 ns^2 / flush time, i.e. the traffic the reference's per-move update would need"}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("k_flush_dram_bytes_per_launch")
-        except Exception:
-            pass
-    # FP64 tensor-pipe roofline of the W re-evaluation (batched inverse + GEMM), the other heavy kernels
+    roofline_update = {"bound": "hbm", "kernel": "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)",
+                       "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                       "traffic": traffic.get("k_flush_wb_dram_bytes_per_walker_flush"),
+                       "walkers_flushed_per_launch": n_flush / max(upd["launches"] // 2, 1), "algorithmic_bytes_per_flush": B_acc,
+                       "avg_launch_us": 1e3 * upd["ms"] / max(upd["launches"] // 2, 1),
+                       "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None,
+                       "rank1_equivalent_GBs": moves_total * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
+                       "note": "traffic is per walker flush (ncu dram bytes / walkers flushed in the captured launch); "
+                               "rank1_equivalent = accepted moves x 16 ns^2 / flush time, the traffic the reference's per-move update would need"}
+    # (2) FP64 tensor-pipe rooflines of the W re-evaluation: batched inverse (2 N^3 per matrix) and W = U X (2 ns N^2)
     dmma_peak = eng.fp64_dmma_peak_tflops()
     n_refresh = res["n_refresh"] / world
     Nh = ns // 2
-    flop_refresh = 2.0 * (2.0 * Nh ** 3 + 2.0 * ns * Nh ** 2)      # inverse + U*X for both species
-    t_ref = (tm["refresh_inverse"]["ms"] + tm["refresh_gemm"]["ms"]) * 1e-3
-    roofline_refresh = {"bound": "tensor", "kernel": "k_inverse_blocked + k_gemm_W_dmma (FP64 DMMA)",
-                        "achieved": n_refresh * flop_refresh / t_ref / 1e12 if t_ref > 0 else 0.0, "peak": dmma_peak,
-                        "peak_source": "measured in this run by kdsl_bench_fp64_dmma (MEASURED_PEAKS.json has no FP64 figure)",
-                        "unit": "TFLOP/s", "frac": (n_refresh * flop_refresh / t_ref / 1e12 / dmma_peak) if t_ref > 0 and dmma_peak > 0 else None,
-                        "algorithmic_flop_per_walker_refresh": flop_refresh, "walker_refreshes": n_refresh,
-                        "kernel_share_of_step": (tm["refresh_inverse"]["ms"] + tm["refresh_gemm"]["ms"]) / ms if ms > 0 else None}
+    dsrc = "measured in this run by kdsl_bench_fp64_dmma (MEASURED_PEAKS.json has no FP64 figure)"
+
+    def tensor_roofline(kernel, flop_per_refresh, t_ms, traffic_key):
+        t = t_ms * 1e-3
+        ach = n_refresh * flop_per_refresh / t / 1e12 if t > 0 else 0.0
+        return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": dmma_peak, "peak_source": dsrc, "unit": "TFLOP/s",
+                "frac": ach / dmma_peak if dmma_peak > 0 else None, "traffic": traffic.get(traffic_key),
+                "algorithmic_flop_per_walker_refresh": flop_per_refresh, "walker_refreshes_per_step": n_refresh / max(K, 1),
+                "avg_launch_us": 1e3 * t_ms / max(2 * K, 1), "kernel_share_of_step": t_ms / ms if ms > 0 else None}
+
+    roofline_inverse = tensor_roofline("k_inverse_v4 (batched blocked Gauss-Jordan inverse of tilde_U, FP64 DMMA trailing update)",
+                                       2.0 * 2.0 * Nh ** 3, tm["refresh_inverse"]["ms"], "k_inverse_v4_dram_bytes_per_matrix")
+    roofline_gemm = tensor_roofline("k_gemm_W_dmma (W = U inv(tilde_U), FP64 DMMA; algorithmic flops as the reference computes it)",
+                                    2.0 * 2.0 * ns * Nh ** 2, tm["refresh_gemm"]["ms"], "k_gemm_W_dmma_dram_bytes_per_matrix")
+    # `roofline` = the kernel with the largest share of the timed step
+    cands = [roofline_inverse, roofline_update, roofline_gemm]
+    roofline = max(cands, key=lambda r: r["kernel_share_of_step"] or 0.0)
 
     # ---- e2e: same work through the public API with HOST buffers (replayed proposal stream) ----
     e2e = None
@@ -322,7 +332,7 @@ def run_ours(args):
     roofline_rank1 = {"bound": "hbm", "kernel": "k_update_ldg (immediate rank-1 update, one move per walker, timed alone)",
                       "achieved": r1, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": r1 / peak,
                       "moves_per_launch": t1["moves"] / max(t1["launches"], 1), "algorithmic_bytes_per_move": B_acc}
-    eng.set_option("update_variant", 1)
+    eng.set_option("update_variant", 2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -344,8 +354,9 @@ def run_ours(args):
             "config": {"workload": workload_name(args.lattice, nw), "sweeps_per_step": n_occ, "walkers_total": total_walkers,
                        "l2": "inputs_exceed_l2 (W working set %.1f GB per GPU)" % (nw * ns * ns * 8 / 1e9),
                        "thermalization_sweeps": therm, "rng": "Xoshiro256++ per walker on device",
-                       "w_update": "delayed rank-k (flush at 16 pending factors); refresh at the reference cadence n_occ"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_refresh": roofline_refresh,
+                       "w_update": "delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates); refresh at the reference cadence n_occ"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_w_update": roofline_update,
+            "roofline_refresh_inverse": roofline_inverse, "roofline_refresh_gemm": roofline_gemm,
             "roofline_rank1_update": roofline_rank1, "e2e": e2e, "cpu_baseline": cpu,
             "observables": {"E_per_site": res["energy"], "acc": res["acc"], "n_OL": res["n_OL"], "n_singular": res["n_singular"]},
             "kernel_ms": {k: round(v["ms"], 3) for k, v in tm.items()},

@@ -271,6 +271,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
         }
         k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
         CK(cudaGetLastError());
+        h->t_launch[KDSL_T_REFRESH_INVERSE] += 2;          // (the span counted one of the three launches)
     }
     {
         Span sp(h, KDSL_T_REFRESH_GEMM);
@@ -304,6 +305,7 @@ int launch_flush_wb_kernel(kdsl_handle h, const int *list, int *cptr) {
     }
     k_flush_finish_wb<<<1, 1024, 0, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
     CK(cudaGetLastError());
+    h->t_launch[KDSL_T_UPDATE] += 1;
     return KDSL_OK;
 }
 
