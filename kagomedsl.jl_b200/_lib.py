@@ -27,7 +27,7 @@ N_TIMERS = len(TIMER_NAMES)
 
 # every symbol include/kdsl.h declares (tests check the library exports exactly these)
 SYMBOLS = (
-    "kdsl_version", "kdsl_last_error", "kdsl_device_count", "kdsl_create", "kdsl_destroy",
+    "kdsl_version", "kdsl_last_error", "kdsl_device_count", "kdsl_create", "kdsl_create_c128", "kdsl_is_complex", "kdsl_destroy",
     "kdsl_set_config", "kdsl_get_config", "kdsl_set_rng", "kdsl_get_rng", "kdsl_set_sweeps",
     "kdsl_get_sweeps", "kdsl_refresh", "kdsl_sweep", "kdsl_replay", "kdsl_measure", "kdsl_last_OL",
     "kdsl_accumulators", "kdsl_reset_accumulators", "kdsl_get_W", "kdsl_set_W", "kdsl_update_W",
@@ -71,6 +71,8 @@ def lib():
         L.kdsl_last_error.restype = C.c_char_p
         vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
         L.kdsl_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, i32]
+        L.kdsl_create_c128.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, i32]
+        L.kdsl_is_complex.argtypes = [vp, vp]
         L.kdsl_destroy.argtypes = [vp]
         L.kdsl_set_config.argtypes = [vp, vp, vp]
         L.kdsl_get_config.argtypes = [vp, vp, vp]

@@ -21,6 +21,7 @@
 #include "kdsl_delayed.cuh"
 #include "kdsl_woodbury.cuh"
 #include "kdsl_update.cuh"
+#include "kdsl_complex.cuh"
 
 #define KDSL_VERSION_NUM 110
 #define KDSL_KTH 16          /* pending factors that trigger a flush */
@@ -75,6 +76,7 @@ struct kdsl_handle_s {
     int64_t sweeps = 0;
     int parity = 0;
     bool have_config = false, W_valid = false;
+    bool cplx = false;            // ComplexF64 mode (kdsl_create_c128): W, U, staging and workspace hold (re, im) pairs
     int64_t walker_sweeps = 0;
     // options
     int64_t refresh_every = 0;
@@ -174,6 +176,11 @@ int launch_update(kdsl_handle h, int parity) {
     const size_t smem = (size_t)(S.ns + CH) * sizeof(double);
     int per_sm = h->update_ctas_per_sm > 0 ? h->update_ctas_per_sm : 4;
     Span sp(h, KDSL_T_UPDATE);
+    if (h->cplx) {
+        k_update_c<256><<<h->num_sms * per_sm, 256, (size_t)S.ns * 2 * sizeof(double), h->stream>>>(S, parity, tiles_up, tiles_dn, CH);
+        CK(cudaGetLastError());
+        return KDSL_OK;
+    }
     k_update_ldg<256, 8><<<h->num_sms * per_sm, 256, smem, h->stream>>>(S, parity, tiles_up, tiles_dn, CH);
     CK(cudaGetLastError());
     return KDSL_OK;
@@ -246,6 +253,33 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
 int launch_refresh(kdsl_handle h, const int *list) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
+    if (h->cplx) {
+        {
+            Span sp(h, KDSL_T_REFRESH_GATHER);
+            k_gather_tilde_c<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+            CK(cudaGetLastError());
+        }
+        {
+            Span sp(h, KDSL_T_REFRESH_INVERSE);
+            const size_t smem = (size_t)Nmax * (4 * sizeof(double) + sizeof(int));
+            CK(cudaFuncSetAttribute(k_inverse_gj_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            k_inverse_gj_c<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_up, 0, h->status);
+            CK(cudaGetLastError());
+            k_inverse_gj_c<<<S.nw, 256, smem, h->stream>>>(S, list, h->A_dn, 1, h->status);
+            CK(cudaGetLastError());
+            k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
+            CK(cudaGetLastError());
+            h->t_launch[KDSL_T_REFRESH_INVERSE] += 2;
+        }
+        {
+            Span sp(h, KDSL_T_REFRESH_GEMM);
+            constexpr int BM = 64, BN = 32;
+            const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
+            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
+            CK(cudaGetLastError());
+        }
+        return KDSL_OK;
+    }
     const bool fast = h->inverse_variant != 1;
     {
         Span sp(h, KDSL_T_REFRESH_GATHER);
@@ -402,6 +436,12 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
                     k_build_factors<KDSL_KMAX><<<h->num_sms * 8, 128, 0, h->stream>>>(S, h->parity);
                     h->parity ^= 1;
                 }
+            } else if (h->cplx) {
+                if (replay)
+                    k_propose_c<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
+                                                                    h->rp_bond + off, have_pick ? h->rp_pick + off : nullptr);
+                else
+                    k_propose_c<false><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, nullptr, nullptr, nullptr);
             } else if (replay) {
                 k_propose<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
                                                               h->rp_bond + off, have_pick ? h->rp_pick + off : nullptr);
@@ -431,6 +471,7 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             Span sp(h, KDSL_T_MEASURE);
             if (woodbury) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, nullptr, 1);
             else if (delayed) k_measure_delayed<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
+            else if (h->cplx) k_measure_c<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             else k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             CK(cudaGetLastError());
         }
@@ -508,8 +549,9 @@ int kdsl_device_count(int *n) {
     return KDSL_OK;
 }
 
-int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
-                const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers) {
+static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
+                       const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers, bool cplx) {
+    const size_t cz = cplx ? 2 : 1;                               // doubles per matrix element
     if (!out) return fail(KDSL_ERR_INVALID_ARGUMENT, "out is null");
     *out = nullptr;
     if (ns <= 0 || (ns & 1)) return fail(KDSL_ERR_INVALID_ARGUMENT, "ns must be positive and even, got %d", ns);
@@ -535,6 +577,8 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
         return fail(KDSL_ERR_CUDA, "device %d is sm_%d%d; libkdsl is built for sm_100a only", device, prop.major, prop.minor);
 
     kdsl_handle h = new kdsl_handle_s();
+    h->cplx = cplx;
+    if (cplx) { h->update_variant = 0; h->inverse_variant = 1; }  // first complex version: the reference's own algorithm
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     DevState &S = h->S;
@@ -560,7 +604,7 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     int *bi, *bj, *adj_off, *adj_nbr;
     double *dUu, *dUd;
     ALLOC(bi, n_bonds); ALLOC(bj, n_bonds); ALLOC(adj_off, ns + 1); ALLOC(adj_nbr, 2 * (size_t)n_bonds);
-    ALLOC(dUu, (size_t)ns * n_up); ALLOC(dUd, (size_t)ns * n_dn);
+    ALLOC(dUu, cz * ns * n_up); ALLOC(dUd, cz * ns * n_dn);
     {
         std::vector<int> hbi(n_bonds), hbj(n_bonds), off(ns + 1, 0), nbr(2 * (size_t)n_bonds);
         for (int b = 0; b < n_bonds; b++) {
@@ -577,25 +621,26 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
         CKD(cudaMemcpy(bj, hbj.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
         CKD(cudaMemcpy(adj_off, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice));
         CKD(cudaMemcpy(adj_nbr, nbr.data(), 2 * (size_t)n_bonds * sizeof(int), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(dUu, U_up, (size_t)ns * n_up * sizeof(double), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(dUd, U_dn, (size_t)ns * n_dn * sizeof(double), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(dUu, U_up, cz * ns * n_up * sizeof(double), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpy(dUd, U_dn, cz * ns * n_dn * sizeof(double), cudaMemcpyHostToDevice));
     }
     S.bi = bi; S.bj = bj; S.adj_off = adj_off; S.adj_nbr = adj_nbr; S.U_up = dUu; S.U_dn = dUd;
     ALLOC(S.kup, nw * ns); ALLOC(S.kdn, nw * ns);
     ALLOC(S.rng, nw * 4); ALLOC(S.zmu, nw);
-    ALLOC(S.W_up, nw * ns * n_up); ALLOC(S.W_dn, nw * ns * n_dn);
-    ALLOC(S.col_up, nw * ns); ALLOC(S.col_dn, nw * ns);
-    ALLOC(S.trow_up, nw * n_up); ALLOC(S.trow_dn, nw * n_dn);
+    ALLOC(S.W_up, cz * nw * ns * n_up); ALLOC(S.W_dn, cz * nw * ns * n_dn);
+    ALLOC(S.col_up, cz * nw * ns); ALLOC(S.col_dn, cz * nw * ns);
+    ALLOC(S.trow_up, cz * nw * n_up); ALLOC(S.trow_dn, cz * nw * n_dn);
     ALLOC(S.acc_list, 12 * nw); ALLOC(S.cnt, 8); ALLOC(S.ref_list, nw); ALLOC(S.flags, nw);
     ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
     ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 4);
     S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;                  // (the buffers are sized for the largest kmax = 32)
-    ALLOC(S.facA_up, nw * KDSL_KALLOC * ns); ALLOC(S.facA_dn, nw * KDSL_KALLOC * ns);
-    ALLOC(S.facB_up, nw * KDSL_KALLOC * ((n_up + 7) / 8 * 8)); ALLOC(S.facB_dn, nw * KDSL_KALLOC * ((n_dn + 7) / 8 * 8));
+    const size_t kal = cplx ? 1 : KDSL_KALLOC;                    // (no delayed updates in complex mode)
+    ALLOC(S.facA_up, nw * kal * ns); ALLOC(S.facA_dn, nw * kal * ns);
+    ALLOC(S.facB_up, nw * kal * ((n_up + 7) / 8 * 8)); ALLOC(S.facB_dn, nw * kal * ((n_dn + 7) / 8 * 8));
     ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw);
     ALLOC(S.wbT, 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
     h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
-    ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
+    ALLOC(h->A_up, cz * nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, cz * nw * h->Np_dn * h->Np_dn);
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
     ALLOC(h->urow, 2 * nw * ns);
     ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
@@ -615,6 +660,22 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
     CKD(cudaFuncSetAttribute(k_inverse_gj, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 #undef CKD
     *out = h;
+    return KDSL_OK;
+}
+
+int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
+                const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers) {
+    return create_impl(out, device, ns, n_up, n_dn, n_bonds, bonds, U_up, U_dn, n_walkers, false);
+}
+
+int kdsl_create_c128(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
+                     const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers) {
+    return create_impl(out, device, ns, n_up, n_dn, n_bonds, bonds, U_up, U_dn, n_walkers, true);
+}
+
+int kdsl_is_complex(kdsl_handle h, int *is_complex) {
+    if (!h || !is_complex) return fail(KDSL_ERR_INVALID_ARGUMENT, "null handle / output");
+    *is_complex = h->cplx ? 1 : 0;
     return KDSL_OK;
 }
 
@@ -780,7 +841,8 @@ int kdsl_measure(kdsl_handle h, double *ol) {
     const DevState &S = h->S;
     {
         Span sp(h, KDSL_T_MEASURE);
-        if (h->update_variant == 2) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, h->d_tmp_d, 0);
+        if (h->cplx) k_measure_c<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+        else if (h->update_variant == 2) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, h->d_tmp_d, 0);
         else k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         CK(cudaGetLastError());
     }
@@ -855,10 +917,10 @@ int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     const DevState &S = h->S;
     if (!out || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / out");
     const int N = spin ? S.n_dn : S.n_up;
-    const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
+    const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N * (h->cplx ? 2 : 1);
     if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyDeviceToHost));
     return KDSL_OK;
 }
 
@@ -868,10 +930,10 @@ int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
     const DevState &S = h->S;
     if (!in || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / in");
     const int N = spin ? S.n_dn : S.n_up;
-    double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N;
+    double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N * (h->cplx ? 2 : 1);
     if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyHostToDevice));
     return KDSL_OK;
 }
 
@@ -897,7 +959,8 @@ int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32
     int *d_mv = nullptr;
     CK(cudaMalloc(&d_mv, mv.size() * sizeof(int)));
     CK(cudaMemcpyAsync(d_mv, mv.data(), mv.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    k_stage_moves<<<grid_for_warps(n_moves), 256, 0, h->stream>>>(S, h->parity, n_moves, d_mv);
+    if (h->cplx) k_stage_moves_c<<<grid_for_warps(n_moves), 256, 0, h->stream>>>(S, h->parity, n_moves, d_mv);
+    else k_stage_moves<<<grid_for_warps(n_moves), 256, 0, h->stream>>>(S, h->parity, n_moves, d_mv);
     CK(cudaGetLastError());
     rc = launch_update(h, h->parity);
     h->parity ^= 1;
@@ -969,6 +1032,12 @@ int kdsl_reset_timers(kdsl_handle h) {
 }
 
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
+    if (h && h->cplx && name) {
+        const std::string nm(name);
+        if ((nm == "update_variant" && value != 0) || (nm == "inverse_variant" && value != 1) || nm == "flush_every" ||
+            nm == "flush_threshold")
+            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (rank-1 updates, unblocked inverse)", name, (long long)value);
+    }
     if (!h || !name) return fail(KDSL_ERR_INVALID_ARGUMENT, "null argument");
     const std::string n(name);
     if (n == "refresh_every") {

@@ -47,14 +47,20 @@ function MC(params::AbstractDict)
     ns = length(ref.kappa_up)
     nw = get(params, :n_walkers, 1)
     dev = get(params, :device, 0)
-    maximum(abs.(imag.(Ham.U_up))) == 0 || error("complex orbitals (B != 0) need the complex-W build")
-    Uu = Matrix{Float64}(real.(Ham.U_up)); Ud = Matrix{Float64}(real.(Ham.U_down))
     bonds = Matrix{Int32}(undef, 2, length(Ham.nn))
     for (b, (i, j)) in enumerate(Ham.nn); bonds[1, b] = i; bonds[2, b] = j; end
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:kdsl_create, libkdsl), Cint,
-                (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Cint),
-                h, dev, ns, Ham.N_up, Ham.N_down, length(Ham.nn), bonds, Uu, Ud, nw))
+    if maximum(abs.(imag.(Ham.U_up))) == 0 && maximum(abs.(imag.(Ham.U_down))) == 0
+        Uu = Matrix{Float64}(real.(Ham.U_up)); Ud = Matrix{Float64}(real.(Ham.U_down))
+        check(ccall((:kdsl_create, libkdsl), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Cint),
+                    h, dev, ns, Ham.N_up, Ham.N_down, length(Ham.nn), bonds, Uu, Ud, nw))
+    else    # Peierls flux B != 0: Matrix{ComplexF64} is exactly the interleaved (re, im) layout of kdsl_create_c128
+        Uu = Matrix{ComplexF64}(Ham.U_up); Ud = Matrix{ComplexF64}(Ham.U_down)
+        check(ccall((:kdsl_create_c128, libkdsl), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint, Ptr{Int32}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint),
+                    h, dev, ns, Ham.N_up, Ham.N_down, length(Ham.nn), bonds, Uu, Ud, nw))
+    end
     mc = MC(Ham, h[], ns, nw, get(params, :sweeps_per_call, 1), 0.0, 0.0)
     finalizer(m -> ccall((:kdsl_destroy, libkdsl), Cint, (Ptr{Cvoid},), m.handle), mc)
     return mc

@@ -121,11 +121,15 @@ class Engine:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         U_up = np.asarray(Ham.U_up)
         U_dn = np.asarray(Ham.U_down)
-        for U in (U_up, U_dn):
-            if np.iscomplexobj(U) and np.abs(U.imag).max(initial=0.0) > 0.0:
-                raise NotImplementedError("complex orbitals (B != 0) are not supported by the FP64 engine yet")
-        self._Uu = np.asfortranarray(U_up.real, dtype=np.float64)
-        self._Ud = np.asfortranarray(U_dn.real, dtype=np.float64)
+        # complex orbitals (Peierls flux B != 0) select the ComplexF64 engine, real ones the FP64 engine
+        self.is_complex = any(np.iscomplexobj(U) and np.abs(U.imag).max(initial=0.0) > 0.0 for U in (U_up, U_dn))
+        self.dtype = np.complex128 if self.is_complex else np.float64
+        if self.is_complex:
+            self._Uu = np.asfortranarray(U_up, dtype=np.complex128)
+            self._Ud = np.asfortranarray(U_dn, dtype=np.complex128)
+        else:
+            self._Uu = np.asfortranarray(U_up.real, dtype=np.float64)
+            self._Ud = np.asfortranarray(U_dn.real, dtype=np.float64)
         self.ns, self.N_up = self._Uu.shape
         self.N_dn = self._Ud.shape[1]
         self.bonds = np.ascontiguousarray(np.asarray(Ham.nn, dtype=np.int32).reshape(-1, 2))
@@ -135,8 +139,9 @@ class Engine:
         self.n_occ = min(self.N_up, self.N_dn)
         self._h = C.c_void_p()
         L = _lib.lib()
-        check(L.kdsl_create(C.byref(self._h), self.device, self.ns, self.N_up, self.N_dn, self.n_bonds,
-                            _ptr(self.bonds), _ptr(self._Uu), _ptr(self._Ud), self.nw))
+        create = L.kdsl_create_c128 if self.is_complex else L.kdsl_create
+        check(create(C.byref(self._h), self.device, self.ns, self.N_up, self.N_dn, self.n_bonds,
+                     _ptr(self.bonds), _ptr(self._Uu), _ptr(self._Ud), self.nw))
         self._L = L
 
     def close(self):
@@ -238,13 +243,13 @@ class Engine:
     # -- inspection / test hooks ---------------------------------------------------------
     def get_W(self, walker: int, spin: int) -> np.ndarray:
         N = self.N_dn if spin else self.N_up
-        out = np.zeros((self.ns, N), order="F")
+        out = np.zeros((self.ns, N), order="F", dtype=self.dtype)
         check(self._L.kdsl_get_W(self._h, int(walker), int(spin), _ptr(out)))
         return out
 
     def set_W(self, walker: int, spin: int, W) -> None:
         N = self.N_dn if spin else self.N_up
-        W = np.asfortranarray(W, dtype=np.float64)
+        W = np.asfortranarray(W, dtype=self.dtype)
         if W.shape != (self.ns, N):
             raise ValueError("DimensionMismatch")
         check(self._L.kdsl_set_W(self._h, int(walker), int(spin), _ptr(W)))

@@ -7,15 +7,15 @@ from oracle import oracle as O
 _cache = {}
 
 
-def problem(n1, n2, PBC=(True, True), antiPBC=(True, False), flux="pi", N_up=None):
-    key = (n1, n2, PBC, antiPBC, flux, N_up)
+def problem(n1, n2, PBC=(True, True), antiPBC=(True, False), flux="pi", N_up=None, B=0.0):
+    key = (n1, n2, PBC, antiPBC, flux, N_up, B)
     if key not in _cache:
         lat = kd.DoubleKagome(1.0, n1, n2, PBC, antiPBC)
         nsites = kd.ns(lat)
         Nu = nsites // 2 if N_up is None else N_up
         Nd = nsites - Nu
         li, lx = (kd.pi_link_in, kd.pi_link_inter) if flux == "pi" else (kd.zero_link_in, kd.zero_link_inter)
-        ham = kd.Hamiltonian(Nu, Nd, lat, link_in=li, link_inter=lx)
+        ham = kd.Hamiltonian(Nu, Nd, lat, link_in=li, link_inter=lx, B=B)
         _cache[key] = (lat, ham)
     return _cache[key]
 

@@ -350,3 +350,96 @@ def test_full_size_invariants(kd, n, nw, n_sweeps):
             assert np.array_equal(Wf[occ], E)                               # exact unit rows
     assert eng.accumulators()[kd._lib.ACC_N_SINGULAR] == 0
     eng.close()
+
+
+# ---- ComplexF64 mode: Peierls flux B != 0, complex Hermitian hopping matrix ----------------
+
+def _complex_problem(kd, n1, n2, B):
+    lat, ham = U.problem(n1, n2, (True, True), (True, False), "pi", None, B)
+    assert np.iscomplexobj(ham.U_up) and np.abs(np.asarray(ham.U_up).imag).max() > 1e-3
+    return lat, ham
+
+
+@pytest.mark.parametrize("n1,n2,B", [(4, 3, 0.37), (6, 6, 0.11)])
+def test_complex_refresh_update_measure_match_oracle(kd, n1, n2, B):
+    lat, ham = _complex_problem(kd, n1, n2, B)
+    ns, nw = kd.ns(lat), 5
+    rng = np.random.default_rng(31)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e4)
+    eng = kd.Engine(ham, nw)
+    assert eng.is_complex
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    orc = U.oracle_walkers(ham, ku, kdn, dtype="c128")
+    ol = eng.measure()
+    for w, mc in enumerate(orc):
+        Wu, Wd = mc.W()
+        assert np.abs(np.asarray(Wu).imag).max() > 1e-6                     # genuinely complex
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+        assert abs(ol[w] - mc.getOL()) < TOL * max(1.0, abs(mc.getOL()))
+    # explicit rank-1 moves (update_W!, src/MonteCarlo.jl:279-292) against the oracle's complex update
+    mv_w, lu, Ku, ld, Kd = [], [], [], [], []
+    for w in range(nw):
+        up_sites = np.nonzero(ku[w])[0]; dn_sites = np.nonzero(kdn[w])[0]
+        i, s = int(up_sites[w % len(up_sites)]), int(dn_sites[(3 * w + 1) % len(dn_sites)])
+        mv_w.append(w); lu.append(int(ku[w][i])); Ku.append(s + 1); ld.append(int(kdn[w][s])); Kd.append(i + 1)
+    eng.update_W(mv_w, lu, Ku, ld, Kd)
+    for w, mc in enumerate(orc):
+        Wu, Wd = mc.W()
+        Wu2 = U.O.update_W(np.array(Wu), lu[w], Ku[w], "c128")
+        Wd2 = U.O.update_W(np.array(Wd), ld[w], Kd[w], "c128")
+        assert U.relerr(eng.get_W(w, 0), Wu2) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd2) < TOL
+    with pytest.raises(kd.KdslError):
+        eng.set_option("update_variant", 2)                                 # delayed updates are real-only for now
+    eng.close()
+
+
+def test_complex_replay_and_device_rng_match_oracle(kd):
+    """ComplexF64 chain: replayed proposals -> kappa / Z_mu / counters bit-exact, W within 1e-10; device Xoshiro ->
+    same trajectory, counters and O_L sums as the oracle's Carlo loop."""
+    lat, ham = _complex_problem(kd, 4, 3, 0.37)
+    ns, nw, n_sweeps = kd.ns(lat), 6, 900
+    rng = np.random.default_rng(8)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=300.0)
+    r = rng.random((n_sweeps, nw))
+    bond = rng.integers(1, len(ham.nn) + 1, size=(n_sweeps, nw)).astype(np.int32)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    eng.replay(r, bond)
+    orc = U.oracle_walkers(ham, ku, kdn, dtype="c128")
+    gku, gkd = eng.get_config()
+    z, zr = eng.Z()
+    for w, mc in enumerate(orc):
+        for s in range(n_sweeps):
+            mc.sweep(replay=(r[s, w], int(bond[s, w]), 1))
+            mc.sweeps = mc.sweeps + 1
+        oku, okd = mc.kappa()
+        assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd)
+        assert z[w] == zr[w] == U.O.Z(ham.nn, oku, okd)
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL and U.relerr(eng.get_W(w, 1), Wd) < TOL
+    acc, acc_w, _ = eng.accumulators(per_walker=True)
+    assert [int(a) for a in acc_w] == [mc.counters()[0] for mc in orc]
+    assert acc[kd._lib.ACC_N_REFRESH] == sum(mc.counters()[2] for mc in orc)
+    eng.close()
+    # device RNG
+    states = kd.walker_states(3, nw)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku, kdn)
+    eng.set_rng(states)
+    eng.refresh()
+    eng.sweep(n_sweeps, thermalization=ns // 2)
+    gku, gkd = eng.get_config()
+    acc, acc_w, ol_w = eng.accumulators(per_walker=True)
+    for w in range(nw):
+        mc = U.O.MC(np.asarray(ham.nn, dtype=np.int32), ham.U_up, ham.U_down, "c128")
+        mc.set_kappa(ku[w], kdn[w]); mc.reevaluateW()
+        st, _ = mc.run(U.O.Xoshiro(states[w]), n_sweeps, ns // 2)
+        oku, okd = mc.kappa()
+        assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd)
+        assert acc_w[w] == st[0]
+        assert abs(ol_w[w] - st[1]) <= 1e-9 * max(1.0, abs(st[1]))
+    eng.close()

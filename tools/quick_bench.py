@@ -19,11 +19,12 @@ def main():
     ap.add_argument("--therm", type=int, default=432)
     ap.add_argument("--opt", action="append", default=[], help="name=value engine options")
     ap.add_argument("--no-prof", action="store_true")
+    ap.add_argument("--B", type=float, default=0.0, help="Peierls flux: B != 0 selects the ComplexF64 engine")
     args = ap.parse_args()
     lat = kd.DoubleKagome(1.0, args.n, args.n, (True, True), (True, False))
     ns = kd.ns(lat)
     t0 = time.time()
-    ham = kd.Hamiltonian(ns // 2, ns // 2, lat)
+    ham = kd.Hamiltonian(ns // 2, ns // 2, lat, B=args.B)
     ku, kdn = kd.init_conf_qr(ham, ns, ns // 2)
     print(f"host setup {time.time()-t0:.2f}s ns={ns} bonds={len(ham.nn)}", flush=True)
     eng = kd.Engine(ham, args.walkers, 0)
@@ -47,7 +48,7 @@ def main():
     tm = eng.timers()
     acc = eng.accumulators()
     ws = args.walkers * args.sweeps
-    B_acc = 16 * ns * ns
+    B_acc = 16 * ns * ns * (2 if eng.is_complex else 1)
     upd = tm["update"]
     print(json.dumps({
         "ns": ns, "walkers": args.walkers, "sweeps": args.sweeps, "wall_s": dt, "walker_sweeps_per_s": ws / dt,
