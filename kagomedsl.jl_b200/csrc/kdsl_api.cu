@@ -18,6 +18,7 @@
 #include "kdsl_refresh_fast.cuh"
 #include "kdsl_inverse_v3.cuh"
 #include "kdsl_inverse_v4.cuh"
+#include "kdsl_inverse_v5.cuh"
 #include "kdsl_delayed.cuh"
 #include "kdsl_woodbury.cuh"
 #include "kdsl_update.cuh"
@@ -207,22 +208,41 @@ int launch_inverse_v3(kdsl_handle h, const int *list, double *A, int spin, int N
     return KDSL_OK;
 }
 
-template <int NB, int RPT, int T, int TP>
+template <int NB, int RPT, int T, int TP, int MINB = 1, int CT = 3>
 int launch_inverse_v4(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     static_assert(RPT * TP >= 8 && TP <= 256, "rows per CTA");
     const size_t smem = ((size_t)2 * NB * Np + NB + 2) * sizeof(double) + ((size_t)12 + NB) * sizeof(int);
-    CK(cudaFuncSetAttribute(k_inverse_v4<NB, RPT, T, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_inverse_v4<NB, RPT, T, TP><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    CK(cudaFuncSetAttribute(k_inverse_v4<NB, RPT, T, TP, MINB, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_v4<NB, RPT, T, TP, MINB, CT><<<h->S.nw, T, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
+template <int NB, int CT>
+int launch_inverse_v5(kdsl_handle h, const int *list, double *A, int spin, int Np) {
+    const size_t smem = ((size_t)3 * NB * Np + NB + 2) * sizeof(double) + ((size_t)12 + NB) * sizeof(int);
+    CK(cudaFuncSetAttribute(k_inverse_v5<NB, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_v5<NB, CT><<<h->S.nw, 512, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
     CK(cudaGetLastError());
     return KDSL_OK;
 }
 
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
-    if (h->inverse_variant == 0) {
+    if (h->inverse_variant == 5 && Np <= 256) {
+        // look-ahead version: pivot loop of panel s+1 concurrent with the DMMA update of step s
+        if (h->inverse_tuning == 1) return launch_inverse_v5<24, 3>(h, list, A, spin, Np);
+        if (h->inverse_tuning == 2) return launch_inverse_v5<32, 2>(h, list, A, spin, Np);
+        if (h->inverse_tuning == 3) return launch_inverse_v5<16, 2>(h, list, A, spin, Np);
+        return launch_inverse_v5<24, 2>(h, list, A, spin, Np);
+    }
+    if (h->inverse_variant == 0 || h->inverse_variant == 4 || h->inverse_variant == 5) {
         // implicit-pivoting blocked Gauss-Jordan, one CTA per matrix and ONE CTA per SM (matrices stay L2 resident)
         if (Np <= 256) {
             if (h->inverse_tuning == 1) return launch_inverse_v4<32, 1, 256, 256>(h, list, A, spin, Np);
-            if (h->inverse_tuning == 2) return launch_inverse_v4<24, 2, 256, 128>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 2) return launch_inverse_v4<24, 1, 256, 256, 2, 2>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 3) return launch_inverse_v4<24, 1, 256, 256, 2, 3>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 4) return launch_inverse_v4<16, 1, 256, 256, 2, 3>(h, list, A, spin, Np);
+            if (h->inverse_tuning == 5) return launch_inverse_v4<24, 1, 256, 256, 1, 2>(h, list, A, spin, Np);
             return launch_inverse_v4<24, 1, 256, 256>(h, list, A, spin, Np);
         }
         if (Np <= 512) return launch_inverse_v4<24, 2, 256, 256>(h, list, A, spin, Np);
@@ -315,7 +335,26 @@ int launch_refresh(kdsl_handle h, const int *list) {
             const int tiles = ((Mmax + 71) / 72) * ((Nmax + 71) / 72);
             const size_t smem = (size_t)4 * 72 * KT * sizeof(double);
             CK(cudaFuncSetAttribute(k_gemm_W_dmma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn), h->urow, S.ns, h->inverse_variant == 0 ? 1 : 0);
+            CK(cudaFuncSetAttribute(k_gemm_W_dmma<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            if (getenv("KDSL_DEBUG_OCC")) {
+                int nb = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm_W_dmma<KT>, 288, smem);
+                fprintf(stderr, "k_gemm_W_dmma: %d CTAs/SM (dynamic smem %zu)\n", nb, smem);
+            }
+            const int perm_k = (h->inverse_variant == 0 || h->inverse_variant == 4 || h->inverse_variant == 5) ? 1 : 0;
+            const int cs = std::max(h->Np_up, h->Np_dn);
+            if (h->gemm_variant == 0 || h->gemm_variant == 2 || h->gemm_variant == 3) {
+                constexpr int ST = 3;
+                const size_t sm3 = (size_t)ST * 2 * 72 * KT * sizeof(double);
+                if (h->gemm_variant == 3) {
+                    CK(cudaFuncSetAttribute(k_gemm_W_cpasync<KT, ST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+                    k_gemm_W_cpasync<KT, ST, 3><<<dim3(tiles, S.nw, 2), 288, sm3, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs, h->urow, S.ns, perm_k);
+                } else {
+                    CK(cudaFuncSetAttribute(k_gemm_W_cpasync<KT, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+                    k_gemm_W_cpasync<KT, ST, 2><<<dim3(tiles, S.nw, 2), 288, sm3, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs, h->urow, S.ns, perm_k);
+                }
+            } else
+            k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn), h->urow, S.ns, perm_k);
         } else {
             constexpr int BM = 64, BN = 64;
             const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);

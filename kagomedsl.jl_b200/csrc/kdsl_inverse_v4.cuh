@@ -22,13 +22,12 @@
 
 // T threads per CTA; the first TP of them own RPT matrix rows each during the panel factorisation (a pivot row is
 // broadcast through shared memory: fewer, fatter threads read it less often).
-template <int NB, int RPT, int T, int TP>
-__global__ void __launch_bounds__(T, 1)
+template <int NB, int RPT, int T, int TP, int MINB = 1, int CT = 3>
+__global__ void __launch_bounds__(T, MINB)
 k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
              int *__restrict__ status, int *__restrict__ colsrc_base, int Np, int cs_stride) {
     constexpr int NWARP = T / 32, PWARP = TP / 32;
     constexpr int KS = NB / 4;                          // DMMA k-steps per panel
-    constexpr int CT = 3;                               // column tiles per warp work item
     static_assert(NB % 8 == 0, "panel width must be a multiple of 8");
     extern __shared__ double sm[];
     const int b = blockIdx.x;

@@ -429,6 +429,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     double *W = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % 3, wn = warp / 3;
+    long long t_phase = clock64();
     if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
     if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
     for (int k = tid; k < 1024 + 32; k += NT) sKp[k] = k < N ? (perm_k ? colsrc[k] : k) : 0;
@@ -466,6 +467,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     load_stage(0);
     store_stage(0);
     __syncthreads();
+    PHASE_TICK(5);
     int buf = 0;
     for (int kk = 0; kk < N; kk += KT) {
         const bool more = kk + KT < N;
@@ -486,6 +488,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
         __syncthreads();
         buf ^= 1;
     }
+    PHASE_TICK(6);
     const int gr = lane >> 2, tg = lane & 3;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -504,10 +507,139 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     const int s_lo = (tm == 0) ? 0 : sRowSite[0];
     const int s_hi = (tm == tiles_m - 1 || sRowSite[TM] < 0) ? ns : sRowSite[TM];
     const int ncols = min(TN, N - n0);
-    for (int x = tid; x < (s_hi - s_lo) * ncols; x += NT) {
-        const int sidx = x % (s_hi - s_lo), cc = x / (s_hi - s_lo);
-        const int site = s_lo + sidx;
+    for (int site = s_lo + tid; site < s_hi; site += NT) {   // one site per thread: its label is read once
         const int l = kap[site];
-        if (l != 0) W[(size_t)(n0 + cc) * ns + site] = (l - 1 == n0 + cc) ? 1.0 : 0.0;
+        if (l != 0) {
+            double *dst = W + (size_t)n0 * ns + site;
+            for (int cc = 0; cc < ncols; cc++) dst[(size_t)cc * ns] = (l - 1 == n0 + cc) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    PHASE_TICK(7);
+}
+
+// cp.async version of k_gemm_W_dmma (gemm_variant 0): the operands go global -> shared memory directly (LDGSTS, 8 bytes
+// per element with zero fill), STAGES stages deep, so no register staging, one barrier per stage and loads in flight
+// across stages.  Same tiling (72x72 per CTA, 3x3 warps of 24x24), fragment-major shared layout, same epilogue.
+__device__ __forceinline__ void cp_async_8(unsigned dst_smem, const void *src, bool valid) {
+    const int sz = valid ? 8 : 0;                          // src-size 0: the 8 destination bytes are zero filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int KT, int STAGES, int MINB>
+__global__ void __launch_bounds__(288, MINB)
+k_gemm_W_cpasync(DevState S, const int *__restrict__ list, const double *__restrict__ X_up,
+                 const double *__restrict__ X_dn, const int *__restrict__ status,
+                 const int *__restrict__ colsrc_base, int Np_up, int Np_dn, int cs_stride,
+                 const int *__restrict__ urow_base, int urow_stride, int perm_k) {
+    constexpr int TM = 72, TN = 72, NT = 288, KS = KT / 4;
+    constexpr int PER = TM * KT / NT;                      // elements of each operand per thread per stage
+    static_assert(TM * KT % NT == 0 && NT % TM == 0 && NT % KT == 0 && TM == TN, "stage must divide evenly");
+    extern __shared__ double gsm[];                        // [STAGES][A: TM*KT | B: TN*KT]
+    __shared__ int sSrc[TN];
+    __shared__ int sRowSite[TM + 1];
+    __shared__ int sKp[1024 + 32];
+    const int b = blockIdx.y, spin = blockIdx.z;
+    if (b >= batch_count(S, list)) return;
+    if (status[2 * b] | status[2 * b + 1]) return;
+    const int w = list ? list[b] : b;
+    const int ns = S.ns, N = spin ? S.n_dn : S.n_up, Np = spin ? Np_dn : Np_up;
+    const int M = ns - N;
+    const int tiles_m = (M + TM - 1) / TM;
+    const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+    const int m0 = tm * TM, n0 = tn * TN;
+    if (n0 >= N) return;
+    const double *U = spin ? S.U_dn : S.U_up;
+    const double *X = (spin ? X_dn : X_up) + (size_t)b * Np * Np;
+    const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
+    const int *urow = urow_base + ((size_t)2 * b + spin) * urow_stride;
+    const int *kap = (spin ? S.kdn : S.kup) + (size_t)w * ns;
+    double *W = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % 3, wn = warp / 3;
+    if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
+    if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
+    for (int k = tid; k < 1024 + 32; k += NT) sKp[k] = k < N ? (perm_k ? colsrc[k] : k) : 0;
+    __syncthreads();
+
+    // element e = tid + q NT of a stage.  A (row r = e % TM, k = e / TM): this thread always serves the same gathered
+    // row of U, k = ka + 4 q, shared offset a_so + 32 q.  B (kb = e % KT, n = e / KT): the same kb, column nb + 12 q.
+    const int a_site = sRowSite[tid % TM], ka = tid / TM;
+    const double *a_ptr = U + (a_site >= 0 ? a_site : 0);
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(gsm);
+    const unsigned a_so = smem0 + 8u * frag_idx(tid % TM, ka, KT);
+    const int kb = tid % KT, nb = tid / KT;
+    unsigned b_so[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) b_so[q] = smem0 + 8u * (TM * KT + frag_idx(nb + (NT / KT) * q, kb, KT));
+    constexpr unsigned STAGE_BYTES = 8u * (TM * KT + TN * KT);
+    auto issue_stage = [&](int kk, int buf) {
+        const unsigned off = buf * STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int k = kk + ka + (NT / TM) * q;
+            const bool va = a_site >= 0 && k < N;
+            cp_async_8(a_so + off + 256u * q, a_ptr + (size_t)sKp[k] * ns, va);
+            const int src = sSrc[nb + (NT / KT) * q];
+            const bool vb = src >= 0 && kk + kb < N;
+            cp_async_8(b_so[q] + off, X + (size_t)(src >= 0 ? src : 0) * Np + kk + kb, vb);
+        }
+    };
+    double c[3][3][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) c[i][j][0] = c[i][j][1] = 0.0;
+    const int nk = (N + KT - 1) / KT;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) issue_stage(s * KT, s);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; it++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (it + STAGES - 1 < nk) issue_stage((it + STAGES - 1) * KT, (it + STAGES - 1) % STAGES);
+        cp_async_commit();
+        const double *sA = gsm + (size_t)(it % STAGES) * (TM * KT + TN * KT);
+        const double *sB = sA + TM * KT;
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            double af[3], bf[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) af[i] = sA[((((wm * 3 + i) * KS) + s) << 5) + lane];
+#pragma unroll
+            for (int j = 0; j < 3; j++) bf[j] = sB[((((wn * 3 + j) * KS) + s) << 5) + lane];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) dmma_8x8x4(c[i][j][0], c[i][j][1], af[i], bf[j]);
+        }
+    }
+    const int gr = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int n = n0 + 24 * wn + 8 * j + 2 * tg + e;
+            if (n >= N) continue;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int site = sRowSite[24 * wm + 8 * i + gr];
+                if (site >= 0) W[(size_t)n * ns + site] = c[i][j][e];
+            }
+        }
+    }
+    const int s_lo = (tm == 0) ? 0 : sRowSite[0];
+    const int s_hi = (tm == tiles_m - 1 || sRowSite[TM] < 0) ? ns : sRowSite[TM];
+    const int ncols = min(TN, N - n0);
+    for (int site = s_lo + tid; site < s_hi; site += NT) {   // one site per thread: its label is read once
+        const int l = kap[site];
+        if (l != 0) {
+            double *dst = W + (size_t)n0 * ns + site;
+            for (int cc = 0; cc < ncols; cc++) dst[(size_t)cc * ns] = (l - 1 == n0 + cc) ? 1.0 : 0.0;
+        }
     }
 }
