@@ -228,7 +228,7 @@ int launch_inverse_v5(kdsl_handle h, const int *list, double *A, int spin, int N
 }
 
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
-    if (h->inverse_variant == 5 && Np <= 256) {
+    if ((h->inverse_variant == 0 || h->inverse_variant == 5) && Np <= 256) {
         // look-ahead version: pivot loop of panel s+1 concurrent with the DMMA update of step s
         if (h->inverse_tuning == 1) return launch_inverse_v5<24, 3>(h, list, A, spin, Np);
         if (h->inverse_tuning == 2) return launch_inverse_v5<32, 2>(h, list, A, spin, Np);
@@ -343,7 +343,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
             }
             const int perm_k = (h->inverse_variant == 0 || h->inverse_variant == 4 || h->inverse_variant == 5) ? 1 : 0;
             const int cs = std::max(h->Np_up, h->Np_dn);
-            if (h->gemm_variant == 0 || h->gemm_variant == 2 || h->gemm_variant == 3) {
+            if (h->gemm_variant == 2 || h->gemm_variant == 3) {   // cp.async pipeline (measured slightly slower than the register-staged kernel)
                 constexpr int ST = 3;
                 const size_t sm3 = (size_t)ST * 2 * 72 * KT * sizeof(double);
                 if (h->gemm_variant == 3) {

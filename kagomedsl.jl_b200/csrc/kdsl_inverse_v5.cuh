@@ -241,27 +241,44 @@ k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
     if (sIdx[1]) return;                                // singular
     gather_X(0, min(NB, Np));
     __syncthreads();
+    long long t_phase = clock64();
+#define V5_TICK(idx, thr)                                                            \
+    do {                                                                             \
+        if (blockIdx.x == 0 && threadIdx.x == (thr)) {                               \
+            const long long now_ = clock64();                                        \
+            g_inv_phase_cycles[idx] += now_ - t_phase;                               \
+            t_phase = now_;                                                          \
+        }                                                                            \
+    } while (0)
     for (int k0 = 0, s = 0; k0 < Np; k0 += NB, s++) {
         const int kw = min(NB, Np - k0);                // multiple of 8
         const int k1 = k0 + kw, kn = min(NB, Np - k1);  // next panel (kn <= 0: none)
         const double *sM = sMb + (size_t)(s & 1) * NB * Np;
         double *sMn = sMb + (size_t)((s + 1) & 1) * NB * Np;
         const int exn = (kw + max(kn, 0)) >> 3;
+        if (blockIdx.x == 0 && tid == 256) t_phase = clock64();
+        V5_TICK(4, 0);                                  // (loop overhead)
         if (kn > 0) {
             update_next_panel(sM, k1 >> 3, kn >> 3);
             __syncthreads();
         }
+        V5_TICK(0, 0);
+        if (blockIdx.x == 0 && tid == 256) t_phase = clock64();
         if (teamP) {
             if (kn > 0) factor_panel(k1, kn, sMn);
+            V5_TICK(1, 0);
         } else {
             update_cols(sM, (Np >> 3) - exn, k0 >> 3, exn, warp - 8, GW);
+            V5_TICK(2, 256);
         }
         __syncthreads();
+        V5_TICK(5, 0);                                  // team P waiting for team G
         if (sIdx[1]) return;
         if (kn > 0) {
             gather_X(k1, kn);
             __syncthreads();
         }
+        V5_TICK(3, 0);
     }
     // ---- index map for the consumer: colsrc[i] = elimination step at which row i was the pivot ----
     int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
