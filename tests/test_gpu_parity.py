@@ -316,7 +316,7 @@ def test_launch_grouping_and_flush_cadence_do_not_change_the_chain(kd, options):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("n,nw,n_sweeps", [(12, 48, 500), (18, 6, 1000)])
+@pytest.mark.parametrize("n,nw,n_sweeps", [(8, 24, 400), (10, 16, 400), (12, 48, 500), (18, 6, 1000)])
 def test_full_size_invariants(kd, n, nw, n_sweeps):
     """BASELINE configs 3 and 4 (432 / 972 sites): size-independent properties instead of an oracle replay.
     W tilde_U = U (the definition of W), unit rows at occupied sites, incremental Z_mu == recount, and after a chain
