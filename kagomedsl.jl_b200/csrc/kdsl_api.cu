@@ -218,11 +218,11 @@ int launch_inverse_v4(kdsl_handle h, const int *list, double *A, int spin, int N
     return KDSL_OK;
 }
 
-template <int NB, int CT>
+template <int NB, int CT, int GW = 8>
 int launch_inverse_v5(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     const size_t smem = ((size_t)3 * NB * Np + NB + 2) * sizeof(double) + ((size_t)12 + NB) * sizeof(int);
-    CK(cudaFuncSetAttribute(k_inverse_v5<NB, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_inverse_v5<NB, CT><<<h->S.nw, 512, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
+    CK(cudaFuncSetAttribute(k_inverse_v5<NB, CT, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_inverse_v5<NB, CT, GW><<<h->S.nw, 256 + 32 * GW, smem, h->stream>>>(h->S, list, A, spin, h->status, h->colsrc, Np, std::max(h->Np_up, h->Np_dn));
     CK(cudaGetLastError());
     return KDSL_OK;
 }
@@ -230,12 +230,12 @@ int launch_inverse_v5(kdsl_handle h, const int *list, double *A, int spin, int N
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     if ((h->inverse_variant == 0 || h->inverse_variant == 5) && Np <= 256) {
         // look-ahead version: pivot loop of panel s+1 concurrent with the DMMA update of step s
-        if (h->inverse_tuning == 1) return launch_inverse_v5<24, 3>(h, list, A, spin, Np);
-        if (h->inverse_tuning == 2) return launch_inverse_v5<32, 2>(h, list, A, spin, Np);
-        if (h->inverse_tuning == 3) return launch_inverse_v5<16, 2>(h, list, A, spin, Np);
+        if ((h->inverse_tuning & 15) == 1) return launch_inverse_v5<24, 3>(h, list, A, spin, Np);
+        if ((h->inverse_tuning & 15) == 2) return launch_inverse_v5<32, 2>(h, list, A, spin, Np);
+        if ((h->inverse_tuning & 15) == 3) return launch_inverse_v5<16, 2>(h, list, A, spin, Np);
         return launch_inverse_v5<24, 2>(h, list, A, spin, Np);
     }
-    if (h->inverse_variant == 0 || h->inverse_variant == 4 || h->inverse_variant == 5) {
+    if (h->inverse_variant == 0 || h->inverse_variant >= 4) {
         // implicit-pivoting blocked Gauss-Jordan, one CTA per matrix and ONE CTA per SM (matrices stay L2 resident)
         if (Np <= 256) {
             if (h->inverse_tuning == 1) return launch_inverse_v4<32, 1, 256, 256>(h, list, A, spin, Np);
@@ -341,7 +341,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm_W_dmma<KT>, 288, smem);
                 fprintf(stderr, "k_gemm_W_dmma: %d CTAs/SM (dynamic smem %zu)\n", nb, smem);
             }
-            const int perm_k = (h->inverse_variant == 0 || h->inverse_variant == 4 || h->inverse_variant == 5) ? 1 : 0;
+            const int perm_k = (h->inverse_variant == 0 || h->inverse_variant >= 4) ? 1 : 0;
             const int cs = std::max(h->Np_up, h->Np_dn);
             if (h->gemm_variant == 2 || h->gemm_variant == 3) {   // cp.async pipeline (measured slightly slower than the register-staged kernel)
                 constexpr int ST = 3;

@@ -10,6 +10,10 @@
 //                                                                                           -> __syncthreads
 //   C. all threads gather X_{s+1} = A[p_q, :] (every column is now up to date)             -> __syncthreads
 // The mathematics, the pivot rule and the stored layout (implicit row pivoting, colsrc) are those of k_inverse_v4.
+// Measured (432 sites, tools/inv_phases.py): team P alone needs 214 k cycles per matrix, 330 k while team G runs --
+// DMMA and DFMA share the FP64 pipe, so every FP64 instruction on the pivot chain queues behind 16-cycle DMMAs; the
+// overlap is worth 5-9 % over k_inverse_v4, not the 40 % a contention-free overlap would give (a two-level panel with
+// 8 instead of NB DFMAs per pivot and a 4-warp team G were tried and did not change that).
 #pragma once
 #include "kdsl_common.cuh"
 #include "kdsl_refresh.cuh"
@@ -17,11 +21,11 @@
 
 __device__ __forceinline__ void bar_team_p() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int NB, int CT>
-__global__ void __launch_bounds__(512, 1)
+template <int NB, int CT, int GW = 8>
+__global__ void __launch_bounds__(256 + 32 * GW, 1)
 k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
              int *__restrict__ status, int *__restrict__ colsrc_base, int Np, int cs_stride) {
-    constexpr int T = 512, TP = 256, GW = 8;            // threads, team-P threads, team-G warps
+    constexpr int T = 256 + 32 * GW, TP = 256, NWARPS = 8 + GW;   // threads, team-P threads (team G: GW warps)
     constexpr int KS = NB / 4;
     static_assert(NB % 8 == 0, "panel width must be a multiple of 8");
     extern __shared__ double sm[];
@@ -218,7 +222,7 @@ k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
     };
     // ---- phase A: the kn column tiles of the next panel (first tile nt0), all 16 warps: item = (tile, row chunk) ----
     auto update_next_panel = [&](const double *sM, int nt0, int kn) {
-        const int nchunks = 16 / kn;
+        const int nchunks = NWARPS / kn;
         const int c = warp % kn, chunk = warp / kn;
         if (chunk >= nchunks) return;
         const int ct = nt0 + c;

@@ -12,7 +12,7 @@ out = (C.c_longlong * 8)()
 names = ["1 panel load", "2 panel LU", "3 publish+moves", "4 columns (U_K, pivot rows)", "5 panel cols", "6 GEMM update"]
 # (variant 0 = k_inverse_v4 has four phases: load, pivot loop, publish + gather, GEMM update)
 eng.set_option('gemm_variant', 1)
-for variant, tuning in ((5, 0), (0, 0)):
+for variant, tuning in ((5, 0), (4, 0)):
     eng.set_option("inverse_variant", variant)
     eng.set_option("inverse_tuning", tuning)
     eng.refresh()
@@ -24,7 +24,7 @@ for variant, tuning in ((5, 0), (0, 0)):
     err = np.abs(eng.get_W(3, 1) - W_ref).max()
     print("variant %d tuning %d: cycles per matrix (CTA 0) total %.0f  |dW| vs first %.2e" % (variant, tuning, v.sum(), err))
     print("   " + "  ".join("%s=%.0f" % (nme.split()[0] + nme.split()[1][:5], c) for nme, c in zip(names, v)))
-    if variant == 5:
+    if variant in (5, 6):
         print("    v5 (per matrix): phase A %.0f  team P factor %.0f  team G update %.0f (measured by warp 8)  gather %.0f  loop %.0f  P waits for G %.0f" % (v[0], v[1], v[2], v[3], v[4], v[5]))
     print("   ", {k: round(x["ms"], 3) for k, x in eng.timers().items() if x["ms"] > 0})
     g = np.array(out[5:8], dtype=float) / (2 * nw)
