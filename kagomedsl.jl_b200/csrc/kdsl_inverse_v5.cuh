@@ -21,6 +21,18 @@
 
 __device__ __forceinline__ void bar_team_p() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// 1 / a to about 1 ulp with THREE dependent FP64 instructions after the MUFU seed x0 (relative error e ~ 2^-20 from
+// rcp.approx.ftz.f64):  1/a = x0 (1 + e + e^2 + ...),  x = x0 + x0 (e + e^2), error e^3 ~ 2^-60.  The compiler's IEEE
+// division is a longer dependent chain plus a slow-path call; on the pivot chain every FP64 instruction queues behind
+// the other team's DMMAs, so the length matters.  (Pivots below 2^-1039 never get here: they flag the matrix singular.)
+__device__ __forceinline__ double rcp_fast(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    const double e = fma(-a, x, 1.0);
+    const double t = fma(e, e, e);
+    return fma(x, t, x);
+}
+
 template <int NB, int CT, int GW = 8>
 __global__ void __launch_bounds__(256 + 32 * GW, 1)
 k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
@@ -80,9 +92,11 @@ k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
             const bool valid = has_row && !pivoted;
             const unsigned hi = valid ? ((unsigned)__double2hiint(a[0]) & 0x7fffffffu) : 0u;
             const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-            double my_rinv = 1.0 / (valid ? a[0] : 1.0);     // speculative; LAPACK getf2 scales by the reciprocal pivot
+            double my_rinv = rcp_fast(valid ? a[0] : 1.0);      // speculative; LAPACK getf2 scales by the reciprocal pivot
             asm volatile("" : "+d"(my_rinv));
             if (pend) apply_pending();
+            double my_s = my_rinv * a[1];                        // ... and the scaled next-column entry of my row (now up to date)
+            asm volatile("" : "+d"(my_s));
             const unsigned win = __ballot_sync(0xffffffffu, valid && hi == mhi);
             const bool leader = win != 0u && lane == __ffs(win) - 1;
             if (lane == 0) sKey[warp] = (win != 0u) ? ((mhi & 0xfffffff8u) | (unsigned)(7 - warp)) : 0u;
@@ -102,25 +116,26 @@ k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
                 sIdx[0] = tid;
                 sPivRow[k] = tid;
                 sRinv[0] = my_rinv;
+                sRinv[1] = my_s;
                 double2 *dst = reinterpret_cast<double2 *>(sRow);
 #pragma unroll
                 for (int j = 0; j < NB; j += 2) dst[j >> 1] = make_double2(a[j], a[j + 1]);
             }
             bar_team_p();
             const int p = sIdx[0];
-            const double rinv = sRinv[0];
-            const double prow1 = sRow[1];
+            const double2 rs = *reinterpret_cast<const double2 *>(sRinv);   // (1 / pivot, pivot row's next entry / pivot)
             if (has_row && tid == p) {
                 pivoted = true;
                 pend_p = true;
                 gstep = k0 + k;
                 mypiv = k;
-                tail = rinv;
-                a[0] = a[1] * rinv;
+                tail = rs.x;
+                a[0] = rs.y;
             } else {
                 pend_p = false;
-                tail = -(a[0] * rinv);
-                a[0] = fma(tail, prow1, a[1]);
+                const double a0 = a[0];
+                a[0] = fma(-a0, rs.y, a[1]);             // the ONE FP64 instruction between the barrier and the next search
+                tail = -(a0 * rs.x);
             }
             pend = true;
         }
