@@ -19,6 +19,7 @@
 #include "kdsl_inverse_v3.cuh"
 #include "kdsl_inverse_v4.cuh"
 #include "kdsl_inverse_v5.cuh"
+#include "kdsl_reeval_fused.cuh"
 #include "kdsl_delayed.cuh"
 #include "kdsl_woodbury.cuh"
 #include "kdsl_update.cuh"
@@ -66,6 +67,13 @@ struct kdsl_handle_s {
     int *colsrc = nullptr;        // [nw][2][Np] column map of the pivoted inverse
     int *urow = nullptr;          // [nw][2][ns] sites not occupied by the species (non-trivial rows of W)
     int Np_up = 0, Np_dn = 0;     // tilde_U dimensions padded to a multiple of 8
+    // fused re-evaluation (k_reeval_fused): transposed U with padding rows, one workspace per resident CTA
+    double *UT_up = nullptr, *UT_dn = nullptr;
+    double *ws_fused = nullptr;
+    size_t ws_stride = 0;
+    size_t fused_smem = 0;        // dynamic shared memory of k_reeval_fused (0: the fused kernel does not apply)
+    int fused_NpMax = 0, fused_CpMax = 0;
+    int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
     double *d_acc8 = nullptr;     // [8]
@@ -298,6 +306,24 @@ int launch_refresh(kdsl_handle h, const int *list) {
             k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->A_up, h->A_dn, h->status);
             CK(cudaGetLastError());
         }
+        return KDSL_OK;
+    }
+    if ((h->inverse_variant == 0 || h->inverse_variant == 6) && h->fused_smem > 0) {
+        // one kernel: Gauss-Jordan on [tilde_U^T | V^T] carries V^T to the non-trivial rows of W (kdsl_reeval_fused.cuh)
+        Span sp(h, KDSL_T_REFRESH_INVERSE);
+        const int v = h->inverse_tuning & 15;
+        const int fgrid = h->fused_ctas > 0 ? std::min(h->fused_ctas, h->num_sms) : h->num_sms;
+        if (v == 1) k_reeval_fused<24, 1, 8><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        else if (v == 2) k_reeval_fused<24, 2, 4><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        else if (v == 3) k_reeval_fused<24, 2, 8><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        else if (v == 4) k_reeval_fused<24, 3, 4><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        else if (v == 8) k_reeval_fused<24, 2, 6, 1><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        else if (v == 9) k_reeval_fused<24, 2, 6, 2><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        else k_reeval_fused<24, 2, 6><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        CK(cudaGetLastError());
+        k_refresh_status_fused<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
+        CK(cudaGetLastError());
+        h->t_launch[KDSL_T_REFRESH_INVERSE] += 1;
         return KDSL_OK;
     }
     const bool fast = h->inverse_variant != 1;
@@ -683,6 +709,33 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
     ALLOC(h->urow, 2 * nw * ns);
     ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
+    if (!cplx && h->Np_up <= 256 && h->Np_dn <= 256) {
+        // fused re-evaluation: shared-memory budget for NB = 24 (operands R - E twice, pivot rows, output staging, tables)
+        constexpr int NB = 24;
+        const int Mp_up = (ns - n_up + 7) / 8 * 8, Mp_dn = (ns - n_dn + 7) / 8 * 8;
+        const int NpMax = std::max(h->Np_up, h->Np_dn), CpMax = std::max(h->Np_up + Mp_up, h->Np_dn + Mp_dn);
+        const size_t smem = ((size_t)2 * NB * NpMax + (size_t)NB * CpMax + (size_t)8 * ns + NB + 2) * sizeof(double) +
+                            ((size_t)12 + 8 + 4 + NB + 32 + NpMax + CpMax + ns) * sizeof(int);
+        if (smem <= (size_t)prop.sharedMemPerBlockOptin && Mp_up <= 256 && Mp_dn <= 256 && ns <= 512) {
+            h->fused_smem = smem;
+            h->fused_NpMax = NpMax;
+            h->fused_CpMax = CpMax;
+            h->ws_stride = std::max((size_t)h->Np_up * (h->Np_up + Mp_up), (size_t)h->Np_dn * (h->Np_dn + Mp_dn));
+            ALLOC(h->UT_up, (size_t)(ns + 9) * h->Np_up); ALLOC(h->UT_dn, (size_t)(ns + 9) * h->Np_dn);
+            ALLOC(h->ws_fused, (size_t)h->num_sms * h->ws_stride);
+            k_build_UT<<<64, 256, 0, h->stream>>>(dUu, h->UT_up, ns, n_up, h->Np_up);
+            k_build_UT<<<64, 256, 0, h->stream>>>(dUd, h->UT_dn, ns, n_dn, h->Np_dn);
+            CKD(cudaGetLastError());
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CKD(cudaStreamSynchronize(h->stream));
+        }
+    }
 #undef ALLOC
     // default xoshiro states must not be all-zero: seed walker w with a fixed SplitMix64 stream
     {
@@ -1128,6 +1181,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         h->S.kmax = fe + kth;
     }
     else if (n == "gemm_variant") h->gemm_variant = (int)value;
+    else if (n == "fused_ctas") h->fused_ctas = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
     return KDSL_OK;

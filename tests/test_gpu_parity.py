@@ -47,7 +47,7 @@ def test_refresh_matches_oracle(kd, n1, n2, PBC, anti, flux):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_refresh_imbalanced_filling_and_variants(kd, variant):
     """N_up != N_down (scripts/FP.jl), N not a multiple of 8; blocked DMMA inverse (0) and simple kernels (1)"""
     lat, ham = U.problem(4, 3, N_up=20)
