@@ -36,7 +36,7 @@ UNIT = "walker-sweeps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lattice", type=int, default=12, help="n1 = n2 (12 -> 432 sites)")
@@ -144,41 +144,66 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 50 ms from before the warm-up; every line is stamped on arrival, and only the samples
+    that fall inside the timed window are reported (all of them taken under load)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.lines = []
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
         except Exception:
             self.p = None
 
-    def stop(self):
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append((time.time(), ln))
+
+    def stop(self, t0, t1):
+        """samples with arrival time in [t0, t1] (the timed region); if the region was too short for three samples,
+        the window is widened backwards over the warm-up steps (same load) and the JSON says so"""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.p.terminate()
         try:
-            out, _ = self.p.communicate(timeout=5)
+            self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+
+        def parse(lo, hi):
+            sm, mx, pw, reasons = [], [], [], set()
+            for ts, ln in list(self.lines):
+                if ts < lo or ts > hi:
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                try:
+                    pw.append(float(f[2]))
+                except ValueError:
+                    pass
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, pw, reasons
+        window = "timed region"
+        sm, mx, pw, reasons = parse(t0, t1 + 0.06)
+        if len(sm) < 3:
+            window = "warm-up + timed region (the timed region alone is shorter than three 50 ms samples)"
+            sm, mx, pw, reasons = parse(self.t_load if hasattr(self, "t_load") else 0.0, t1 + 0.06)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def run_ours(args):
@@ -214,9 +239,13 @@ def run_ours(args):
     ctx = kd.MCContext({"thermalization": 0, "seed": args.seed})
     therm = args.thermalization if args.thermalization >= 0 else 10 * ns
     therm = (therm // n_occ) * n_occ                    # keep the bin phase aligned
+    sampler = ClockSampler(local) if rank == 0 else None
     eng.sweeps = 0
     eng.sweep(therm, -1)
     ctx.sweeps = therm
+    eng.synchronize()
+    if sampler:
+        sampler.t_load = time.time()                    # from here on the GPU runs the timed workload (warm-up steps)
     for _ in range(W):                                  # warm-up steps through the public API
         kd.run_(mc, ctx, n_occ)
     eng.synchronize()
@@ -225,16 +254,17 @@ def run_ours(args):
     eng.set_profiling(True)                             # CUDA events around every launch on the engine's stream
 
     # ---- timed region: K steps, device-timed on the launching stream, max over ranks ----
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    t_w0 = time.time()
     eng.event_record(0)
     for _ in range(K):
         kd.run_(mc, ctx, n_occ)
     eng.event_record(1)
     eng.synchronize()
+    t_w1 = time.time()
     barrier()
     ms = allmax(eng.event_elapsed_ms(0, 1))
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_w0, t_w1) if sampler else None
     tm = eng.timers()
     eng.set_profiling(False)
     res = kd.accumulators(mc)                            # NCCL all-reduce of the observable accumulators
@@ -276,25 +306,45 @@ def run_ours(args):
     Nh = ns // 2
     dsrc = "measured in this run by kdsl_bench_fp64_dmma (MEASURED_PEAKS.json has no FP64 figure)"
 
-    def tensor_roofline(kernel, flop_per_refresh, t_ms, traffic_key, reference_flop=None):
+    # algorithmic flop of one walker refresh (both species) = the reference's inverse + full product
+    flop_survey = 2.0 * (2.0 * Nh ** 3 + 2.0 * ns * Nh ** 2)
+
+    def tensor_roofline(kernel, flop_executed, t_ms, launches, traffic_key, flop_algorithmic):
         t = t_ms * 1e-3
-        ach = n_refresh * flop_per_refresh / t / 1e12 if t > 0 else 0.0
+        ach = n_refresh * flop_algorithmic / t / 1e12 if t > 0 else 0.0
+        exe = n_refresh * flop_executed / t / 1e12 if t > 0 else 0.0
         return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": dmma_peak, "peak_source": dsrc, "unit": "TFLOP/s",
                 "frac": ach / dmma_peak if dmma_peak > 0 else None, "traffic": traffic.get(traffic_key),
-                "algorithmic_flop_per_walker_refresh": flop_per_refresh,
-                "reference_flop_per_walker_refresh": reference_flop if reference_flop is not None else flop_per_refresh,
+                "algorithmic_flop_per_walker_refresh": flop_algorithmic, "executed_flop_per_walker_refresh": flop_executed,
+                "executed_tflops": exe, "executed_frac": exe / dmma_peak if dmma_peak > 0 else None,
                 "walker_refreshes_per_step": n_refresh / max(K, 1),
-                "avg_launch_us": 1e3 * t_ms / max(2 * K, 1), "kernel_share_of_step": t_ms / ms if ms > 0 else None}
+                "avg_launch_us": 1e3 * t_ms / max(launches, 1), "kernel_share_of_step": t_ms / ms if ms > 0 else None}
 
-    roofline_inverse = tensor_roofline("k_inverse_v4 (batched blocked Gauss-Jordan inverse of tilde_U, FP64 DMMA trailing update)",
-                                       2.0 * 2.0 * Nh ** 3, tm["refresh_inverse"]["ms"], "k_inverse_v4_dram_bytes_per_matrix")
-    # (the rows of W on occupied sites are unit vectors and are written, not computed: the kernel executes
-    #  2 (ns - N) N^2 flops per matrix where the reference's full product has 2 ns N^2; `achieved` counts executed flops)
-    roofline_gemm = tensor_roofline("k_gemm_W_dmma (W = U inv(tilde_U) on the unoccupied rows, FP64 DMMA)",
-                                    2.0 * 2.0 * (ns - Nh) * Nh ** 2, tm["refresh_gemm"]["ms"], "k_gemm_W_dmma_dram_bytes_per_matrix",
-                                    reference_flop=2.0 * 2.0 * ns * Nh ** 2)
+    fused = tm["refresh_gemm"]["launches"] == 0 and tm["refresh_inverse"]["launches"] > 0
+    if fused:
+        # k_reeval_fused: Gauss-Jordan on [tilde_U^T | V^T] (N x (N + M), M = ns - N unoccupied sites): step k touches the
+        # N rows of the N - k - 1 + M unfinished columns -> executed flop per matrix = sum_k 2 N (N - k - 1 + M) ~ 3 N^3.
+        # `achieved` follows the contract (SURVEY 8(d) per-walker figure = what the reference computes: 2 (2 N^3 + 2 ns N^2));
+        # `executed_*` is what the kernel really issues (the unit rows and the explicit inverse are never computed).
+        M_un = ns - Nh
+        flop_exec = 2.0 * sum(2.0 * Nh * (Nh - k - 1 + M_un) for k in range(Nh))
+        roofline_refresh = tensor_roofline(
+            "k_reeval_fused (reevaluateW!: blocked Gauss-Jordan on [tilde_U^T | V^T] with look-ahead, FP64 DMMA, writes W directly)",
+            flop_exec, tm["refresh_inverse"]["ms"], tm["refresh_inverse"]["launches"] // 2,
+            "k_reeval_fused_dram_bytes_per_walker_refresh", flop_survey)
+        roofline_inverse, roofline_gemm = roofline_refresh, None
+        cands = [roofline_refresh, roofline_update]
+    else:
+        roofline_inverse = tensor_roofline("k_inverse_v5 / k_inverse_v4 (batched blocked Gauss-Jordan inverse of tilde_U, FP64 DMMA trailing update)",
+                                           2.0 * 2.0 * Nh ** 3, tm["refresh_inverse"]["ms"], 2 * K, "k_inverse_v4_dram_bytes_per_matrix",
+                                           2.0 * 2.0 * Nh ** 3)
+        # (the rows of W on occupied sites are unit vectors and are written, not computed: the kernel executes
+        #  2 (ns - N) N^2 flops per matrix where the reference's full product has 2 ns N^2)
+        roofline_gemm = tensor_roofline("k_gemm_W_dmma (W = U inv(tilde_U) on the unoccupied rows, FP64 DMMA)",
+                                        2.0 * 2.0 * (ns - Nh) * Nh ** 2, tm["refresh_gemm"]["ms"], 2 * K,
+                                        "k_gemm_W_dmma_dram_bytes_per_matrix", 2.0 * 2.0 * ns * Nh ** 2)
+        cands = [roofline_inverse, roofline_update, roofline_gemm]
     # `roofline` = the kernel with the largest share of the timed step
-    cands = [roofline_inverse, roofline_update, roofline_gemm]
     roofline = max(cands, key=lambda r: r["kernel_share_of_step"] or 0.0)
 
     # ---- e2e: same work through the public API with HOST buffers (replayed proposal stream) ----
@@ -359,9 +409,10 @@ def run_ours(args):
             "config": {"workload": workload_name(args.lattice, nw), "sweeps_per_step": n_occ, "walkers_total": total_walkers,
                        "l2": "inputs_exceed_l2 (W working set %.1f GB per GPU)" % (nw * ns * ns * 8 / 1e9),
                        "thermalization_sweeps": therm, "rng": "Xoshiro256++ per walker on device",
-                       "w_update": "delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates); refresh at the reference cadence n_occ"},
+                       "w_update": "delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates); refresh at the reference cadence n_occ",
+                       "refresh": "k_reeval_fused (one kernel)" if fused else "gather + inverse + GEMM kernels"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_w_update": roofline_update,
-            "roofline_refresh_inverse": roofline_inverse, "roofline_refresh_gemm": roofline_gemm,
+            "roofline_refresh": roofline_inverse, "roofline_refresh_gemm": roofline_gemm,
             "roofline_rank1_update": roofline_rank1, "e2e": e2e, "cpu_baseline": cpu,
             "observables": {"E_per_site": res["energy"], "acc": res["acc"], "n_OL": res["n_OL"], "n_singular": res["n_singular"]},
             "kernel_ms": {k: round(v["ms"], 3) for k, v in tm.items()},

@@ -72,7 +72,9 @@ struct kdsl_handle_s {
     double *ws_fused = nullptr;
     size_t ws_stride = 0;
     size_t fused_smem = 0;        // dynamic shared memory of k_reeval_fused (0: the fused kernel does not apply)
-    int fused_NpMax = 0, fused_CpMax = 0;
+    int fused_NpMax = 0, fused_CpMax = 0, fused_NB = 24, fused_stage = 0;
+    size_t fused_smem24 = 0, fused_smem16 = 0;   // the same for panel widths 24 (default) and 16
+    int fused_stage24 = 0, fused_stage16 = 0;
     int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
@@ -313,13 +315,22 @@ int launch_refresh(kdsl_handle h, const int *list) {
         Span sp(h, KDSL_T_REFRESH_INVERSE);
         const int v = h->inverse_tuning & 15;
         const int fgrid = h->fused_ctas > 0 ? std::min(h->fused_ctas, h->num_sms) : h->num_sms;
-        if (v == 1) k_reeval_fused<24, 1, 8><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
-        else if (v == 2) k_reeval_fused<24, 2, 4><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
-        else if (v == 3) k_reeval_fused<24, 2, 8><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
-        else if (v == 4) k_reeval_fused<24, 3, 4><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
-        else if (v == 8) k_reeval_fused<24, 2, 6, 1><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
-        else if (v == 9) k_reeval_fused<24, 2, 6, 2><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
-        else k_reeval_fused<24, 2, 6><<<fgrid, 512, h->fused_smem, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax);
+        const bool nb32 = h->fused_NB == 32 && (v == 6 || v == 7);   // wider panels: fewer passes, but a longer pivot chain (measured slower)
+        const size_t fsm = nb32 ? h->fused_smem : v == 5 ? h->fused_smem16 : h->fused_smem24;
+        const int fst = nb32 ? h->fused_stage : v == 5 ? h->fused_stage16 : h->fused_stage24;
+#define KDSL_FUSED_LAUNCH(...) k_reeval_fused<__VA_ARGS__><<<fgrid, 512, fsm, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax, fst)
+        if (nb32) {
+            if (v == 7) KDSL_FUSED_LAUNCH(32, 2, 4);
+            else KDSL_FUSED_LAUNCH(32, 2, 6);
+        } else if (v == 1) KDSL_FUSED_LAUNCH(24, 1, 8);
+        else if (v == 2) KDSL_FUSED_LAUNCH(24, 2, 4);
+        else if (v == 3) KDSL_FUSED_LAUNCH(24, 2, 8);
+        else if (v == 4) KDSL_FUSED_LAUNCH(24, 3, 4);
+        else if (v == 5) KDSL_FUSED_LAUNCH(16, 2, 6);
+        else if (v == 8) KDSL_FUSED_LAUNCH(24, 2, 6, 1);
+        else if (v == 9) KDSL_FUSED_LAUNCH(24, 2, 6, 2);
+        else KDSL_FUSED_LAUNCH(24, 2, 6);
+#undef KDSL_FUSED_LAUNCH
         CK(cudaGetLastError());
         k_refresh_status_fused<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
         CK(cudaGetLastError());
@@ -710,14 +721,22 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     ALLOC(h->urow, 2 * nw * ns);
     ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
     if (!cplx && h->Np_up <= 256 && h->Np_dn <= 256) {
-        // fused re-evaluation: shared-memory budget for NB = 24 (operands R - E twice, pivot rows, output staging, tables)
-        constexpr int NB = 24;
+        // fused re-evaluation: shared-memory budget (operands R - E twice, pivot rows, output staging, tables) for panel
+        // width NB; the staging area is dropped when the idle R - E buffer can hold 8 columns of W for both species
         const int Mp_up = (ns - n_up + 7) / 8 * 8, Mp_dn = (ns - n_dn + 7) / 8 * 8;
-        const int NpMax = std::max(h->Np_up, h->Np_dn), CpMax = std::max(h->Np_up + Mp_up, h->Np_dn + Mp_dn);
-        const size_t smem = ((size_t)2 * NB * NpMax + (size_t)NB * CpMax + (size_t)8 * ns + NB + 2) * sizeof(double) +
-                            ((size_t)12 + 8 + 4 + NB + 32 + NpMax + CpMax + ns) * sizeof(int);
-        if (smem <= (size_t)prop.sharedMemPerBlockOptin && Mp_up <= 256 && Mp_dn <= 256 && ns <= 512) {
-            h->fused_smem = smem;
+        const int NpMax = std::max(h->Np_up, h->Np_dn), NpMin = std::min(h->Np_up, h->Np_dn);
+        const int CpMax = std::max(h->Np_up + Mp_up, h->Np_dn + Mp_dn);
+        auto budget = [&](int NB, int *stage) {
+            *stage = (NB * NpMin >= 8 * ns && !getenv("KDSL_NO_ALIAS")) ? 0 : 8 * ns;
+            return ((size_t)2 * NB * NpMax + (size_t)NB * CpMax + (size_t)*stage + NB + 2) * sizeof(double) +
+                   ((size_t)12 + 8 + 4 + NB + 32 + NpMax + CpMax + ns + 1) * sizeof(int);
+        };
+        const size_t smem24 = budget(24, &h->fused_stage24), smem32 = budget(32, &h->fused_stage);
+        if (smem24 <= (size_t)prop.sharedMemPerBlockOptin && Mp_up <= 256 && Mp_dn <= 256 && ns <= 512) {
+            h->fused_smem24 = smem24;
+            h->fused_smem16 = budget(16, &h->fused_stage16);
+            if (smem32 <= (size_t)prop.sharedMemPerBlockOptin) { h->fused_smem = smem32; h->fused_NB = 32; }
+            else { h->fused_smem = smem24; h->fused_stage = h->fused_stage24; h->fused_NB = 24; }
             h->fused_NpMax = NpMax;
             h->fused_CpMax = CpMax;
             h->ws_stride = std::max((size_t)h->Np_up * (h->Np_up + Mp_up), (size_t)h->Np_dn * (h->Np_dn + Mp_dn));
@@ -726,13 +745,18 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             k_build_UT<<<64, 256, 0, h->stream>>>(dUu, h->UT_up, ns, n_up, h->Np_up);
             k_build_UT<<<64, 256, 0, h->stream>>>(dUd, h->UT_dn, ns, n_dn, h->Np_dn);
             CKD(cudaGetLastError());
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int optin = (int)smem24;                 // exact sizes: a larger limit changes the L1 carve-out the driver picks
+            const int optin32 = (int)std::min(smem32, (size_t)prop.sharedMemPerBlockOptin);
+            CKD(cudaFuncSetAttribute(k_reeval_fused<32, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin32));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin32));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaStreamSynchronize(h->stream));
         }
     }

@@ -59,6 +59,44 @@ __global__ void k_refresh_status_fused(DevState S, const int *__restrict__ list,
     }
 }
 
+
+// Workspace traffic carries an L2 evict_last policy (the per-CTA workspace is re-read and re-written at every block step
+// and should outlive the streams passing through the L2: W output, transposed U, the other kernels' data) and does not
+// allocate in L1.
+#ifndef KDSL_FUSED_L2HINT
+#define KDSL_FUSED_L2HINT 1
+#endif
+__device__ __forceinline__ unsigned long long fused_policy_keep() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double2 ws_ld2(const double2 *a, unsigned long long p) {
+#if KDSL_FUSED_L2HINT
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(p));
+    return v;
+#else
+    return __ldcg(a);
+#endif
+}
+__device__ __forceinline__ double ws_ld1(const double *a, unsigned long long p) {
+#if KDSL_FUSED_L2HINT
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(p));
+    return v;
+#else
+    return __ldcg(a);
+#endif
+}
+__device__ __forceinline__ void ws_st2(double2 *a, double2 v, unsigned long long p) {
+#if KDSL_FUSED_L2HINT
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(a), "d"(v.x), "d"(v.y), "l"(p) : "memory");
+#else
+    __stcg(a, v);
+#endif
+}
+
 // Shared-memory carve-up and the per-item context.  The phases below are separate device functions that rebuild
 // their pointers from the kernel parameters (constant bank) and re-read the item context from shared memory, so that
 // nothing but the loop counters is live across the latency-critical pivot loop (one monolithic scope cost the pivot
@@ -78,8 +116,7 @@ struct FusedSmem {
     __device__ __forceinline__ FusedSmem(double *sm, int NpMax, int CpMax, int ns) {
         sMb = sm;                                           // [2][NpMax x NB] frag-major (r = row, k = q): R - E
         sX = sMb + (size_t)2 * NB * NpMax;                  // [CpMax x NB] frag-major (r = column, k = q): B[p_q, column]
-        sStg = sX + (size_t)NB * CpMax;                     // [8][ns] output staging of the last step: 8 columns of W
-        sRow = sStg + (size_t)8 * ns;                       // [NB] the pivot row of the current step
+        sRow = sX + (size_t)NB * CpMax;                     // [NB] the pivot row of the current step
         sRinv = sRow + NB;                                  // [2]
         ctx = reinterpret_cast<FusedCtx *>(sRinv + 2);      // (48 bytes reserved)
         sKey = reinterpret_cast<unsigned *>(sRinv + 2 + 6); // [8] per-warp candidate keys
@@ -89,6 +126,9 @@ struct FusedSmem {
         sStep = sScan + 32;                                 // [NpMax] elimination step at which row j was the pivot
         sColSite = sStep + NpMax;                           // [CpMax] row of UT behind column c of B
         sSiteInfo = sColSite + CpMax;                       // [ns] >= 0: index u of an unoccupied site, < 0: -label
+        // [8][ns] output staging of the last step (8 columns of W), only allocated when the idle R - E buffer is
+        // too small for it; last so that no other offset depends on it
+        sStg = reinterpret_cast<double *>(sSiteInfo + ns + ((NB + NpMax + CpMax + ns) & 1));
     }
 };
 static_assert(sizeof(FusedCtx) <= 48, "FusedCtx must fit its reserved slot");
@@ -105,6 +145,8 @@ template <int NB, bool FIRST>
 __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double *__restrict__ ws, int k0, int kw,
                                                    double *sM, bool pivoted) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
+    const unsigned long long pol = fused_policy_keep();
+    (void)pol;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Np = L.ctx->Np, Cp = L.ctx->Cp;
     const bool has_row = tid < Np;
@@ -118,7 +160,7 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
         const double2 *src = reinterpret_cast<const double2 *>(ws + (size_t)tid * Cp + k0);
 #pragma unroll
         for (int c = 0; c < NB; c += 2) {
-            const double2 v = (has_row && c < kw) ? __ldcg(src + (c >> 1)) : make_double2(0.0, 0.0);
+            const double2 v = (has_row && c < kw) ? ws_ld2(src + (c >> 1), pol) : make_double2(0.0, 0.0);
             a[c] = v.x;
             a[c + 1] = v.y;
         }
@@ -227,6 +269,8 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
 template <int NB, int T, bool FIRST>
 __device__ __noinline__ void fused_gather_X(const FusedArgs FA, const double *__restrict__ ws, int c_lo, int kw) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
+    const unsigned long long pol = fused_policy_keep();
+    (void)pol;
     constexpr int KS = NB / 4;
     const int Np = L.ctx->Np, Cp = L.ctx->Cp;
     const double *UT = L.ctx->UT;
@@ -240,7 +284,7 @@ __device__ __noinline__ void fused_gather_X(const FusedArgs FA, const double *__
             for (int e = 0; e < 4; e++) v[e] = (q + e < kw) ? __ldcg(col + L.sPivRow[q + e]) : 0.0;
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; e++) v[e] = (q + e < kw) ? __ldcg(ws + (size_t)L.sPivRow[q + e] * Cp + j) : 0.0;
+            for (int e = 0; e < 4; e++) v[e] = (q + e < kw) ? ws_ld1(ws + (size_t)L.sPivRow[q + e] * Cp + j, pol) : 0.0;
         }
         double2 *dst = reinterpret_cast<double2 *>(L.sX + frag_idx(j, q, NB));
         dst[0] = make_double2(v[0], v[1]);
@@ -256,6 +300,8 @@ template <int NB, int CT, int D, bool FIRST>
 __device__ __noinline__ void fused_update_cols(const FusedArgs FA, double *__restrict__ ws, const double *sM,
                                                   int t_lo, int t_hi, int w_team, int nw_team, int ns) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
+    const unsigned long long pol = fused_policy_keep();
+    (void)pol;
     constexpr int KS = NB / 4;
     const int lane = threadIdx.x & 31;
     const int gr = lane >> 2, tg = lane & 3;
@@ -298,7 +344,7 @@ __device__ __noinline__ void fused_update_cols(const FusedArgs FA, double *__res
         _Pragma("unroll") for (int c = 0; c < CT; c++) {                                                       \
             if (!cv[c]) (d_)[c] = make_double2(0.0, 0.0);                                                      \
             else if (FIRST) (d_)[c] = make_double2(__ldcg(u0p[c] + (rl_ << 3)), __ldcg(u1p[c] + (rl_ << 3)));   \
-            else (d_)[c] = __ldcg(reinterpret_cast<const double2 *>(rp + (size_t)(rl_ << 3) * Cp + c * 8));     \
+            else (d_)[c] = ws_ld2(reinterpret_cast<const double2 *>(rp + (size_t)(rl_ << 3) * Cp + c * 8), pol);     \
         }                                                                                                      \
     } while (0)
 #define FUSED_TILE(rt_, d_)                                                                                    \
@@ -308,7 +354,7 @@ __device__ __noinline__ void fused_update_cols(const FusedArgs FA, double *__res
         _Pragma("unroll") for (int s = 0; s < KS; s++)                                                         \
             _Pragma("unroll") for (int c = 0; c < CT; c++) dmma_8x8x4((d_)[c].x, (d_)[c].y, mf[s], xf[c][s]);   \
         _Pragma("unroll") for (int c = 0; c < CT; c++)                                                         \
-            if (cv[c]) __stcg(reinterpret_cast<double2 *>(rp + (size_t)((rt_) << 3) * Cp + c * 8), (d_)[c]);    \
+            if (cv[c]) ws_st2(reinterpret_cast<double2 *>(rp + (size_t)((rt_) << 3) * Cp + c * 8), (d_)[c], pol);    \
     } while (0)
 #pragma unroll
         for (int i = 0; i < D; i++) FUSED_LD(i, buf[i]);
@@ -336,8 +382,10 @@ __device__ __noinline__ void fused_update_cols(const FusedArgs FA, double *__res
 //      column sStep[..] of W -- as full, aligned, coalesced segments (thread = site; unit rows of the occupied sites
 //      filled in on the way; every 32-byte sector is written whole, so the L2 never has to fetch one to merge). ----
 template <int NB, int D, bool FIRST>
-__device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *__restrict__ ws, const double *sM, int ns) {
+__device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *__restrict__ ws, const double *sM, double *stage, int ns) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
+    const unsigned long long pol = fused_policy_keep();
+    (void)pol;
     constexpr int KS = NB / 4, CT = 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gr = lane >> 2, tg = lane & 3;
@@ -346,7 +394,6 @@ __device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *_
     const double *UT = L.ctx->UT;
     double *W = L.ctx->W;
     const int *sColSite = L.sColSite, *sStep = L.sStep;
-    double *stage = L.sStg;
     const int t_lo = Np >> 3, nct = (Cp >> 3) - t_lo;        // V part: nct column tiles, <= 32 (host check)
     const int t0 = t_lo + warp * CT;
     double xf[CT][KS];
@@ -379,7 +426,7 @@ __device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *_
         _Pragma("unroll") for (int c = 0; c < CT; c++) {                                                       \
             if (!cv[c]) (d_)[c] = make_double2(0.0, 0.0);                                                      \
             else if (FIRST) (d_)[c] = make_double2(__ldcg(u0p[c] + (rl_ << 3)), __ldcg(u1p[c] + (rl_ << 3)));   \
-            else (d_)[c] = __ldcg(reinterpret_cast<const double2 *>(rp + (size_t)(rl_ << 3) * Cp + c * 8));     \
+            else (d_)[c] = ws_ld2(reinterpret_cast<const double2 *>(rp + (size_t)(rl_ << 3) * Cp + c * 8), pol);     \
         }                                                                                                      \
     } while (0)
 #define FUSED_TILE(rt_, d_)                                                                                    \
@@ -427,6 +474,8 @@ template <int NB, bool FIRST>
 __device__ __noinline__ void fused_update_next_panel(const FusedArgs FA, double *__restrict__ ws, const double *sM,
                                                         int c0, int kn) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
+    const unsigned long long pol = fused_policy_keep();
+    (void)pol;
     constexpr int KS = NB / 4, NT = NB / 8, NWARPS = 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gr = lane >> 2, tg = lane & 3;
@@ -456,7 +505,7 @@ __device__ __noinline__ void fused_update_next_panel(const FusedArgs FA, double 
         for (int c = 0; c < NT; c++) {
             if (rt >= nrt || c >= nt) d[i][c] = make_double2(0.0, 0.0);
             else if (FIRST) d[i][c] = make_double2(__ldcg(u0p[c] + (rt << 3)), __ldcg(u1p[c] + (rt << 3)));
-            else d[i][c] = __ldcg(reinterpret_cast<const double2 *>(rp + (size_t)(rt << 3) * Cp + c * 8));
+            else d[i][c] = ws_ld2(reinterpret_cast<const double2 *>(rp + (size_t)(rt << 3) * Cp + c * 8), pol);
         }
     }
 #pragma unroll
@@ -472,7 +521,7 @@ __device__ __noinline__ void fused_update_next_panel(const FusedArgs FA, double 
                 for (int c = 0; c < NT; c++) dmma_8x8x4(d[i][c].x, d[i][c].y, mf[s], xf[c][s]);
 #pragma unroll
             for (int c = 0; c < NT; c++)
-                if (c < nt) __stcg(reinterpret_cast<double2 *>(rp + (size_t)(rt << 3) * Cp + c * 8), d[i][c]);
+                if (c < nt) ws_st2(reinterpret_cast<double2 *>(rp + (size_t)(rt << 3) * Cp + c * 8), d[i][c], pol);
         }
     }
 }
@@ -484,6 +533,8 @@ __device__ __noinline__ void fused_item_setup(const FusedArgs FA, const DevState
                                                  const double *UT_up, const double *UT_dn, int *__restrict__ status,
                                                  int Np_up, int Np_dn, int item) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
+    const unsigned long long pol = fused_policy_keep();
+    (void)pol;
     constexpr int NWARPS = T / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = item >> 1, spin = item & 1;
@@ -539,7 +590,7 @@ template <int NB, int CT, int DG = 6, int DBG = 0>
 __global__ void __launch_bounds__(512, 1)
 k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws_base, size_t ws_stride,
                const double *__restrict__ UT_up, const double *__restrict__ UT_dn, int *__restrict__ status,
-               int Np_up, int Np_dn, int NpMax, int CpMax) {
+               int Np_up, int Np_dn, int NpMax, int CpMax, int stage_doubles) {
     constexpr int T = 512, NWARPS = 16, GW = 8;
     static_assert(NB % 8 == 0, "panel width must be a multiple of 8");
     extern __shared__ double sm[];
@@ -602,8 +653,10 @@ k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws
                     __syncthreads();
                     FUSED_TICK(3, 0);
                 } else {
-                    if (first) fused_last_step<NB, 4, true>(FA, ws, sM, S.ns);
-                    else fused_last_step<NB, 4, false>(FA, ws, sM, S.ns);
+                    // output staging: the idle R - E buffer when it holds 8 columns of W, else the dedicated area
+                    double *stage = stage_doubles == 0 ? sMn : L.sStg;
+                    if (first) fused_last_step<NB, 4, true>(FA, ws, sM, stage, S.ns);
+                    else fused_last_step<NB, 4, false>(FA, ws, sM, stage, S.ns);
                     FUSED_TICK(6, 0);
                 }
             }

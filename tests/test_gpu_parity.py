@@ -252,6 +252,37 @@ def test_error_paths(kd):
     eng2.close()
 
 
+def test_fused_refresh_singular_species_is_isolated(kd):
+    """k_reeval_fused refreshes the two species independently: a singular tilde_U of one species flags the walker
+    (SingularException, src/MonteCarlo.jl:596-603) and leaves that species' W alone, the other species is re-evaluated"""
+    lat, ham = U.problem(2, 2, (False, False), (False, False))
+    Ud = np.zeros((12, 6)); Ud[:6] = np.eye(6)                  # down orbitals live on sites 1..6 only
+    ham2 = kd.Hamiltonian(6, 6, ham.U_up, Ud, ham.H_mat, ham.nn)
+    rng = np.random.default_rng(5)
+    ku, kdn = U.well_conditioned_mott(rng, ham, 12, 6, 2)
+    # walker 0: down particles on sites 7..12 -> tilde_U_down = 0 (singular); walker 1: on sites 1..6 -> identity
+    for w, dn_sites in enumerate((np.arange(6, 12), np.arange(0, 6))):
+        ku[w] = 0; kdn[w] = 0
+        kdn[w, dn_sites] = np.arange(1, 7)
+        ku[w, np.setdiff1d(np.arange(12), dn_sites)] = np.arange(1, 7)
+    eng = kd.Engine(ham2, 2)
+    eng.set_config(ku, kdn)
+    with pytest.raises(kd.SingularException):
+        eng.refresh()
+    fl = eng.flags()
+    assert fl[0] & 1 and not fl[1] & 1
+    for w in range(2):                                           # the up species is fine for both walkers
+        cond = np.linalg.cond(kd.tilde_U(ham.U_up, ku[w]))
+        if cond < 1e8:
+            mc = U.oracle_walkers(ham2, ku[w:w + 1], kdn[w:w + 1], refresh=False)[0]
+            Wu_ref = ham.U_up @ np.linalg.inv(kd.tilde_U(ham.U_up, ku[w]))
+            assert U.relerr(eng.get_W(w, 0), Wu_ref) < 1e-8 * max(1.0, cond)
+    Wd1 = eng.get_W(1, 1)                                        # walker 1, down: W = U_dn inv(I) = U_dn
+    assert U.relerr(Wd1, Ud) < TOL
+    assert np.all(eng.get_W(0, 1) == 0.0)                        # walker 0, down: never written
+    eng.close()
+
+
 def test_exact_energy_12_sites(kd):
     """<E>/site of the chain's stationary law |psi|^2 / Z_mu on the reference's 2x2 OBC test lattice:
     exact enumeration gives -0.3714938624 (tests/golden/exact_energies.json)"""

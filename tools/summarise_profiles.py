@@ -49,9 +49,10 @@ def stalls(rep, top=14):
 
 def main():
     traffic = {}
-    units = {"inverse": ("k_inverse_v4_dram_bytes_per_matrix", 1024), "gemm": ("k_gemm_W_dmma_dram_bytes_per_matrix", 2048),
+    units = {"fused": ("k_reeval_fused_dram_bytes_per_walker_refresh", 1024),
+             "inverse": ("k_inverse_v4_dram_bytes_per_matrix", 1024), "gemm": ("k_gemm_W_dmma_dram_bytes_per_matrix", 2048),
              "flush": ("k_flush_wb_dram_bytes_per_walker_flush", None)}
-    for name in ("inverse", "gemm", "flush", "decide", "measure", "gather"):
+    for name in ("fused", "inverse", "gemm", "flush", "decide", "measure", "gather"):
         rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (name, TAG))
         if not os.path.exists(rep):
             print("missing", rep)
