@@ -728,7 +728,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
         const int CpMax = std::max(h->Np_up + Mp_up, h->Np_dn + Mp_dn);
         auto budget = [&](int NB, int *stage) {
             *stage = (NB * NpMin >= 8 * ns && !getenv("KDSL_NO_ALIAS")) ? 0 : 8 * ns;
-            return ((size_t)2 * NB * NpMax + (size_t)NB * CpMax + (size_t)*stage + NB + 2) * sizeof(double) +
+            return ((size_t)2 * NB * NpMax + (size_t)NB * CpMax + (size_t)*stage + 2 * NB + 2) * sizeof(double) +
                    ((size_t)12 + 8 + 4 + NB + 32 + NpMax + CpMax + ns + 1) * sizeof(int);
         };
         const size_t smem24 = budget(24, &h->fused_stage24), smem32 = budget(32, &h->fused_stage);

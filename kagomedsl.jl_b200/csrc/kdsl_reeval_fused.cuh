@@ -97,6 +97,27 @@ __device__ __forceinline__ void ws_st2(double2 *a, double2 v, unsigned long long
 #endif
 }
 
+// split barrier for the pivot search (mbarrier in shared memory): every thread of team P arrives as soon as its warp's
+// candidate key is published and waits only after it has applied the pending panel update, so the 22 DFMAs per pivot
+// (which queue behind the other team's DMMAs) no longer sit between the candidates and the decision
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ unsigned long long mbar_arrive(unsigned addr) {
+    unsigned long long tok;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(tok) : "r"(addr) : "memory");
+    return tok;
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned long long tok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra MBAR_WAIT_%=;\n\t"
+        "}" ::"r"(addr), "l"(tok) : "memory");
+}
+
 // Shared-memory carve-up and the per-item context.  The phases below are separate device functions that rebuild
 // their pointers from the kernel parameters (constant bank) and re-read the item context from shared memory, so that
 // nothing but the loop counters is live across the latency-critical pivot loop (one monolithic scope cost the pivot
@@ -117,7 +138,7 @@ struct FusedSmem {
         sMb = sm;                                           // [2][NpMax x NB] frag-major (r = row, k = q): R - E
         sX = sMb + (size_t)2 * NB * NpMax;                  // [CpMax x NB] frag-major (r = column, k = q): B[p_q, column]
         sRow = sX + (size_t)NB * CpMax;                     // [NB] the pivot row of the current step
-        sRinv = sRow + NB;                                  // [2]
+        sRinv = sRow + 2 * NB;                              // [2]   (sRow is double buffered: [2][NB])
         ctx = reinterpret_cast<FusedCtx *>(sRinv + 2);      // (48 bytes reserved)
         sKey = reinterpret_cast<unsigned *>(sRinv + 2 + 6); // [8] per-warp candidate keys
         sIdx = reinterpret_cast<int *>(sKey + 8);           // [4]: [0] pivot row, [1] singular flag
@@ -165,12 +186,13 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
             a[c + 1] = v.y;
         }
     }
-    double *sRow = L.sRow, *sRinv = L.sRinv;
+    double *sRowB = L.sRow, *sRinv = L.sRinv;
     unsigned *sKey = L.sKey;
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(L.sScan + 24);
     int *sIdx = L.sIdx, *sPivRow = L.sPivRow, *sStep = L.sStep;
     double tail = 0.0;
     bool pend = false, pend_p = false;
-    auto apply_pending = [&]() {                    // columns 2.. of the pending step (sRow still holds its pivot row)
+    auto apply_pending = [&](const double *sRow) {   // columns 2.. of the pending step (sRow still holds its pivot row)
         if (!has_row) return;
         const double2 *prow2 = reinterpret_cast<const double2 *>(sRow);
 #pragma unroll
@@ -194,13 +216,14 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
         const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
         double my_rinv = rcp_fast(valid ? a[0] : 1.0);      // speculative reciprocal of my candidate
         asm volatile("" : "+d"(my_rinv));
-        if (pend) apply_pending();
-        double my_s = my_rinv * a[1];                        // scaled next-column entry of my row (now up to date)
-        asm volatile("" : "+d"(my_s));
         const unsigned win = __ballot_sync(0xffffffffu, valid && hi == mhi);
         const bool leader = win != 0u && lane == __ffs(win) - 1;
         if (lane == 0) sKey[warp] = (win != 0u) ? ((mhi & 0xfffffff8u) | (unsigned)(7 - warp)) : 0u;
-        bar_team_p();
+        const unsigned long long tok = mbar_arrive(mbar);   // candidates published ...
+        if (pend) apply_pending(sRowB + ((k + 1) & 1) * NB);  // ... the pending update of step k-1 runs while the others arrive
+        double my_s = my_rinv * a[1];                        // scaled next-column entry of my row (now up to date)
+        asm volatile("" : "+d"(my_s));
+        mbar_wait(mbar, tok);
         unsigned bk;
         {
             const uint4 k0v = *reinterpret_cast<const uint4 *>(sKey);
@@ -218,7 +241,7 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
             sStep[tid] = k0 + k;
             sRinv[0] = my_rinv;
             sRinv[1] = my_s;
-            double2 *dst = reinterpret_cast<double2 *>(sRow);
+            double2 *dst = reinterpret_cast<double2 *>(sRowB + (k & 1) * NB);
 #pragma unroll
             for (int j = 0; j < NB; j += 2) dst[j >> 1] = make_double2(a[j], a[j + 1]);
         }
@@ -243,7 +266,7 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
         if (tid == 0) { sIdx[1] = 1; }
         return pivoted;
     }
-    if (pend) apply_pending();
+    if (pend) apply_pending(sRowB + ((kw + 1) & 1) * NB);
     // publish R - E in fragment order.  After kw rotations register slot cs holds panel column (cs + kw) mod NB
     // (columns >= kw are zero padding).
     if (has_row) {
@@ -347,30 +370,43 @@ __device__ __noinline__ void fused_update_cols(const FusedArgs FA, double *__res
             else (d_)[c] = ws_ld2(reinterpret_cast<const double2 *>(rp + (size_t)(rl_ << 3) * Cp + c * 8), pol);     \
         }                                                                                                      \
     } while (0)
-#define FUSED_TILE(rt_, d_)                                                                                    \
+#define FUSED_MMA(rt_, d_)                                                                                     \
     do {                                                                                                       \
         double mf[KS];                                                                                         \
         _Pragma("unroll") for (int s = 0; s < KS; s++) mf[s] = sM[((((rt_) * KS) + s) << 5) + lane];           \
         _Pragma("unroll") for (int s = 0; s < KS; s++)                                                         \
             _Pragma("unroll") for (int c = 0; c < CT; c++) dmma_8x8x4((d_)[c].x, (d_)[c].y, mf[s], xf[c][s]);   \
-        _Pragma("unroll") for (int c = 0; c < CT; c++)                                                         \
-            if (cv[c]) ws_st2(reinterpret_cast<double2 *>(rp + (size_t)((rt_) << 3) * Cp + c * 8), (d_)[c], pol);    \
     } while (0)
+#define FUSED_ST(rt_, d_)                                                                                      \
+    do {                                                                                                       \
+        _Pragma("unroll") for (int c = 0; c < CT; c++)                                                         \
+            if (cv[c]) ws_st2(reinterpret_cast<double2 *>(rp + (size_t)((rt_) << 3) * Cp + c * 8), (d_)[c], pol); \
+    } while (0)
+#define FUSED_TILE(rt_, d_) do { FUSED_MMA(rt_, d_); FUSED_ST(rt_, d_); } while (0)
 #pragma unroll
         for (int i = 0; i < D; i++) FUSED_LD(i, buf[i]);
         int rt0 = 0;
 #pragma unroll 1
         for (; rt0 + D <= nrt; rt0 += D) {
+            // the store of a tile (and the refill of its registers) is issued after the DMMAs of the NEXT tile: the warp
+            // issues in order, a store right behind its last DMMA would hold the next tile back for the DMMA latency
 #pragma unroll
             for (int i = 0; i < D; i++) {
-                FUSED_TILE(rt0 + i, buf[i]);
-                FUSED_LD(rt0 + i + D, buf[i]);
+                FUSED_MMA(rt0 + i, buf[i]);
+                if (i > 0) {
+                    FUSED_ST(rt0 + i - 1, buf[i - 1]);
+                    FUSED_LD(rt0 + i - 1 + D, buf[i - 1]);
+                }
             }
+            FUSED_ST(rt0 + D - 1, buf[D - 1]);
+            FUSED_LD(rt0 + 2 * D - 1, buf[D - 1]);
         }
         const int rem = nrt - rt0;
 #pragma unroll
         for (int i = 0; i < D - 1; i++)
             if (i < rem) FUSED_TILE(rt0 + i, buf[i]);
+#undef FUSED_MMA
+#undef FUSED_ST
 #undef FUSED_LD
 #undef FUSED_TILE
     }
@@ -598,6 +634,8 @@ k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws
     const FusedArgs FA{sm, NpMax, CpMax, S.ns};
     const int n_items = 2 * batch_count(S, list);
     double *ws = ws_base + (size_t)blockIdx.x * ws_stride;
+    if (threadIdx.x == 0) mbar_init((unsigned)__cvta_generic_to_shared(L.sScan + 24), 256);
+    __syncthreads();
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         fused_item_setup<NB, T>(FA, S, list, UT_up, UT_dn, status, Np_up, Np_dn, item);
