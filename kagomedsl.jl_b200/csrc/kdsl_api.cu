@@ -315,17 +315,14 @@ int launch_refresh(kdsl_handle h, const int *list) {
         Span sp(h, KDSL_T_REFRESH_INVERSE);
         const int v = h->inverse_tuning & 15;
         const int fgrid = h->fused_ctas > 0 ? std::min(h->fused_ctas, h->num_sms) : h->num_sms;
-        const bool nb32 = h->fused_NB == 32 && (v == 6 || v == 7);   // wider panels: fewer passes, but a longer pivot chain (measured slower)
+        const bool nb32 = h->fused_NB == 32 && v == 6;   // wider panels: fewer passes, but a longer pivot chain (measured slower)
         const size_t fsm = nb32 ? h->fused_smem : v == 5 ? h->fused_smem16 : h->fused_smem24;
         const int fst = nb32 ? h->fused_stage : v == 5 ? h->fused_stage16 : h->fused_stage24;
 #define KDSL_FUSED_LAUNCH(...) k_reeval_fused<__VA_ARGS__><<<fgrid, 512, fsm, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax, fst)
         if (nb32) {
-            if (v == 7) KDSL_FUSED_LAUNCH(32, 2, 4);
-            else KDSL_FUSED_LAUNCH(32, 2, 6);
+            KDSL_FUSED_LAUNCH(32, 2, 6);
         } else if (v == 1) KDSL_FUSED_LAUNCH(24, 1, 8);
         else if (v == 2) KDSL_FUSED_LAUNCH(24, 2, 4);
-        else if (v == 3) KDSL_FUSED_LAUNCH(24, 2, 8);
-        else if (v == 4) KDSL_FUSED_LAUNCH(24, 3, 4);
         else if (v == 5) KDSL_FUSED_LAUNCH(16, 2, 6);
         else if (v == 8) KDSL_FUSED_LAUNCH(24, 2, 6, 1);
         else if (v == 9) KDSL_FUSED_LAUNCH(24, 2, 6, 2);
@@ -748,15 +745,12 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             const int optin = (int)smem24;                 // exact sizes: a larger limit changes the L1 carve-out the driver picks
             const int optin32 = (int)std::min(smem32, (size_t)prop.sharedMemPerBlockOptin);
             CKD(cudaFuncSetAttribute(k_reeval_fused<32, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin32));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin32));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-            CKD(cudaFuncSetAttribute(k_reeval_fused<24, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaStreamSynchronize(h->stream));
         }
     }

@@ -254,6 +254,26 @@ k_decide_wb(DevState S, int gate_refresh, int n_sweeps, const double *__restrict
         const unsigned long long *st = S.rng + (size_t)w * 4;
         g.s0 = st[0]; g.s1 = st[1]; g.s2 = st[2]; g.s3 = st[3];
     }
+    // Pull this walker's small state (kappa, the Woodbury T matrices and lists: ~13 KB) towards the SM before the
+    // first proposal needs it: every sweep is a chain of dependent accesses to it, and between two launches the
+    // flush kernel has streamed hundreds of MB through the L2.  One prefetch per 128-byte line, no registers held
+    // (-4 % on the launch; issuing the T loads of the ratio / accept loops in chunks was tried and lost to the spills
+    // under the 64-register cap that keeps all 4096 warps resident).
+    {
+        const char *pk_up = reinterpret_cast<const char *>(S.kup + (size_t)w * S.ns);
+        const char *pk_dn = reinterpret_cast<const char *>(S.kdn + (size_t)w * S.ns);
+        for (int off = lane * 128; off < S.ns * 4; off += 32 * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pk_up + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pk_dn + off));
+        }
+        const char *pT = reinterpret_cast<const char *>(S.wbT + (size_t)w * 2 * S.kmax * S.kmax);
+        for (int off = lane * 128; off < 2 * S.kmax * S.kmax * 8; off += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pT + off));
+        if (lane < 4) {
+            const char *pL = reinterpret_cast<const char *>((lane & 1 ? S.wbL : S.wbK) + (size_t)w * 2 * S.kmax);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pL + (lane >> 1) * 128));
+        }
+    }
     unsigned dirty_up = 0u, dirty_dn = 0u;                          // displaced-particle slots (re)assigned in this launch
     for (int s = 0; s < n_sweeps; s++) {
         const size_t off = (size_t)s * S.nw;
