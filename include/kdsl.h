@@ -210,10 +210,16 @@ int kdsl_set_profiling(kdsl_handle h, int enabled);
 int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_counts);
 int kdsl_reset_timers(kdsl_handle h);
 
-/* Tunables: "refresh_every" (0 = reference cadence n_occ); "update_variant" (1 = delayed rank-k
- * updates, default; 0 = the reference's immediate rank-1 update streamed per accepted move);
- * "update_ctas_per_sm", "update_cols_per_item" (rank-1 kernel tiling); "inverse_variant" / "gemm_variant"
- * (0 = blocked DMMA kernels, 1 = simple cross-check kernels).  KDSL_ERR_INVALID_ARGUMENT if unknown. */
+/* Tunables: "refresh_every" (0 = reference cadence n_occ); "update_variant" (2 = delayed rank-k updates in
+ * Woodbury form, default; 1 = delayed updates with explicit factor lists; 0 = the reference's immediate rank-1
+ * update streamed per accepted move); "flush_every" / "flush_threshold" (Woodbury mode: sweeps between flush
+ * launches / pending updates that make a walker due; sum <= 32); "fuse_sweeps"; "flush_variant";
+ * "update_ctas_per_sm", "update_cols_per_item" (rank-1 kernel tiling);
+ * "inverse_variant": how reevaluateW! (src/MonteCarlo.jl:55-66) is computed -- 0 (default) / 6 = the one-kernel
+ * re-evaluation k_reeval_fused when it applies (N <= 256 per species, ns <= 512), else as 5; 5 / 4 = gather +
+ * blocked implicit-pivoting inverse (with / without look-ahead) + DMMA product; 3, 2 = older blocked inverses;
+ * 1 = simple cross-check kernels.  "inverse_tuning", "gemm_variant", "fused_ctas": developer knobs.
+ * KDSL_ERR_INVALID_ARGUMENT if the name is unknown. */
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);
 
 /*
