@@ -87,6 +87,7 @@ struct kdsl_handle_s {
     int64_t sweeps = 0;
     int parity = 0;
     bool have_config = false, W_valid = false;
+    double *X_up = nullptr, *X_dn = nullptr;   // ComplexF64 mode: un-embedded complex inverses [nw][N*N] (re, im)
     bool cplx = false;            // ComplexF64 mode (kdsl_create_c128): W, U, staging and workspace hold (re, im) pairs
     int64_t walker_sweeps = 0;
     // options
@@ -283,6 +284,38 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
 int launch_refresh(kdsl_handle h, const int *list) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
+    if (h->cplx && h->inverse_variant != 1) {
+        // ComplexF64: inverse of tilde_U through its real 2N x 2N embedding on the production real kernels
+        if (std::max(h->Np_up, h->Np_dn) > 1024)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "ComplexF64 mode supports at most 512 orbitals per species");
+        const int cs = std::max(h->Np_up, h->Np_dn);
+        {
+            Span sp(h, KDSL_T_REFRESH_GATHER);
+            k_gather_tilde_emb_c<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->Np_up, h->Np_dn);
+            CK(cudaGetLastError());
+        }
+        {
+            Span sp(h, KDSL_T_REFRESH_INVERSE);
+            int rc = launch_inverse(h, list, h->A_up, 0, h->Np_up);
+            if (rc) return rc;
+            rc = launch_inverse(h, list, h->A_dn, 1, h->Np_dn);
+            if (rc) return rc;
+            k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
+            CK(cudaGetLastError());
+            h->t_launch[KDSL_T_REFRESH_INVERSE] += 2;
+        }
+        {
+            Span sp(h, KDSL_T_REFRESH_GEMM);
+            k_unembed_c<<<dim3(S.nw, 2), 256, cs * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs);
+            CK(cudaGetLastError());
+            constexpr int BM = 64, BN = 32;
+            const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
+            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status);
+            CK(cudaGetLastError());
+            h->t_launch[KDSL_T_REFRESH_GEMM] += 1;
+        }
+        return KDSL_OK;
+    }
     if (h->cplx) {
         {
             Span sp(h, KDSL_T_REFRESH_GATHER);
@@ -651,7 +684,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
 
     kdsl_handle h = new kdsl_handle_s();
     h->cplx = cplx;
-    if (cplx) { h->update_variant = 0; h->inverse_variant = 1; }  // first complex version: the reference's own algorithm
+    if (cplx) { h->update_variant = 0; h->inverse_variant = 0; }  // complex: the reference's rank-1 updates; inverse through the real embedding
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     DevState &S = h->S;
@@ -712,8 +745,15 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     ALLOC(S.facB_up, nw * kal * ((n_up + 7) / 8 * 8)); ALLOC(S.facB_dn, nw * kal * ((n_dn + 7) / 8 * 8));
     ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw);
     ALLOC(S.wbT, 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
-    h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
-    ALLOC(h->A_up, cz * nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, cz * nw * h->Np_dn * h->Np_dn);
+    if (cplx) {
+        // the refresh workspace holds the real embedding [[X, -Y], [Y, X]] of tilde_U, padded: Np = roundup(2 N, 8)
+        h->Np_up = (2 * n_up + 7) / 8 * 8; h->Np_dn = (2 * n_dn + 7) / 8 * 8;
+        ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
+        ALLOC(h->X_up, 2 * nw * n_up * n_up); ALLOC(h->X_dn, 2 * nw * n_dn * n_dn);
+    } else {
+        h->Np_up = (n_up + 7) / 8 * 8; h->Np_dn = (n_dn + 7) / 8 * 8;
+        ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
+    }
     ALLOC(h->colsrc, 2 * nw * std::max(h->Np_up, h->Np_dn));
     ALLOC(h->urow, 2 * nw * ns);
     ALLOC(h->status, 2 * nw); ALLOC(h->d_tmp_i, 2 * nw); ALLOC(h->d_tmp_d, nw); ALLOC(h->d_acc8, 8);
@@ -1144,9 +1184,9 @@ int kdsl_reset_timers(kdsl_handle h) {
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (h && h->cplx && name) {
         const std::string nm(name);
-        if ((nm == "update_variant" && value != 0) || (nm == "inverse_variant" && value != 1) || nm == "flush_every" ||
+        if ((nm == "update_variant" && value != 0) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5) || nm == "flush_every" ||
             nm == "flush_threshold")
-            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (rank-1 updates, unblocked inverse)", name, (long long)value);
+            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (rank-1 updates; inverse_variant 0/4/5 = real-embedding blocked inverse, 1 = unblocked complex)", name, (long long)value);
     }
     if (!h || !name) return fail(KDSL_ERR_INVALID_ARGUMENT, "null argument");
     const std::string n(name);

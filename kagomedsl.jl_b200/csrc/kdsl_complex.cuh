@@ -339,6 +339,67 @@ k_inverse_gj_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
     }
 }
 
+// ---- inverse of the complex tilde_U through its real embedding (inverse_variant 0 of the ComplexF64 engine) ----
+// A = X + iY (N x N complex) is invertible iff E = [[X, -Y], [Y, X]] (2N x 2N real) is, and inv(E) = [[P, -Q], [Q, P]]
+// with inv(A) = P + iQ.  E goes through the production real kernels (blocked implicit-pivoting Gauss-Jordan on the
+// FP64 tensor pipe, k_inverse_v4 / k_inverse_v5): twice the flops of a complex elimination, but DMMA instead of a
+// latency-bound unblocked loop in global memory (measured 3.4x faster at 432 sites).
+// k_gather_tilde_emb_c: E padded to Ne = roundup(2N, 8) with an identity block; grid (nw, 2), dynamic smem N ints.
+__global__ void __launch_bounds__(256)
+k_gather_tilde_emb_c(DevState S, const int *__restrict__ list, double *__restrict__ E_up, double *__restrict__ E_dn,
+                     int *__restrict__ status, int Ne_up, int Ne_dn) {
+    extern __shared__ int s_site_e[];
+    const int b = blockIdx.x, spin = blockIdx.y;
+    if (b >= batch_count(S, list)) return;
+    const int w = list ? list[b] : b;
+    const int ns = S.ns, N = spin ? S.n_dn : S.n_up, Ne = spin ? Ne_dn : Ne_up;
+    const int *kap = (spin ? S.kdn : S.kup) + (size_t)w * ns;
+    const cplx *U = cW(spin ? S.U_dn : S.U_up, 0);
+    double *E = (spin ? E_dn : E_up) + (size_t)b * Ne * Ne;
+    for (int R = threadIdx.x; R < ns; R += blockDim.x) {
+        const int l = kap[R];
+        if (l != 0) s_site_e[l - 1] = R;
+    }
+    if (threadIdx.x == 0) status[2 * b + spin] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < Ne * Ne; e += blockDim.x) {
+        const int c = e / Ne, r = e - c * Ne;
+        double v;
+        if (r < 2 * N && c < 2 * N) {
+            const int l = r < N ? r : r - N, cc = c < N ? c : c - N;
+            const cplx u = U[(size_t)cc * ns + s_site_e[l]];        // tilde_U[l, cc] = U[R_l, cc]
+            v = (r < N) == (c < N) ? u.x : (r < N ? -u.y : u.y);
+        } else {
+            v = r == c ? 1.0 : 0.0;
+        }
+        E[e] = v;
+    }
+}
+
+// k_unembed_c: the stored result of the implicit-pivoting inverse is S[p_k, c] = inv(E)[k, p_c] (colsrc[i] = step at
+// which row i was the pivot); X[k, j] = (inv(E)[k, j], inv(E)[N + k, j]) as a plain column-major complex N x N matrix
+// for k_gemm_W_c.  grid (nw, 2), dynamic smem Ne ints.
+__global__ void __launch_bounds__(256)
+k_unembed_c(DevState S, const int *__restrict__ list, const double *__restrict__ E_up, const double *__restrict__ E_dn,
+            double *__restrict__ X_up, double *__restrict__ X_dn, const int *__restrict__ status,
+            const int *__restrict__ colsrc_base, int Ne_up, int Ne_dn, int cs_stride) {
+    extern __shared__ int s_row_of_step[];
+    const int b = blockIdx.x, spin = blockIdx.y;
+    if (b >= batch_count(S, list)) return;
+    if (status[2 * b] | status[2 * b + 1]) return;
+    const int N = spin ? S.n_dn : S.n_up, Ne = spin ? Ne_dn : Ne_up;
+    const double *E = (spin ? E_dn : E_up) + (size_t)b * Ne * Ne;
+    cplx *X = cW(spin ? X_dn : X_up, (size_t)b * N * N);
+    const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
+    for (int i = threadIdx.x; i < Ne; i += blockDim.x) s_row_of_step[colsrc[i]] = i;
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int j = e / N, k = e - j * N;
+        const double *col = E + (size_t)colsrc[j] * Ne;
+        X[e] = c_make(col[s_row_of_step[k]], col[s_row_of_step[N + k]]);
+    }
+}
+
 // W[w] (ns x N) = U (ns x N) * X_b (N x N), complex, shared-memory tiled FP64 FMA.  grid (tiles_m * tiles_n, nw, 2).
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(256)

@@ -400,15 +400,20 @@ def test_complex_refresh_update_measure_match_oracle(kd, n1, n2, B):
     eng = kd.Engine(ham, nw)
     assert eng.is_complex
     eng.set_config(ku, kdn)
-    eng.refresh()
     orc = U.oracle_walkers(ham, ku, kdn, dtype="c128")
-    ol = eng.measure()
-    for w, mc in enumerate(orc):
-        Wu, Wd = mc.W()
-        assert np.abs(np.asarray(Wu).imag).max() > 1e-6                     # genuinely complex
-        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
-        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
-        assert abs(ol[w] - mc.getOL()) < TOL * max(1.0, abs(mc.getOL()))
+    # inverse_variant 0 (default): inverse through the real 2N x 2N embedding on the blocked DMMA kernels;
+    # 1: the reference-style unblocked complex Gauss-Jordan
+    for variant in (1, 5, 0):
+        eng.set_option("inverse_variant", variant)
+        eng.set_W(0, 0, np.zeros_like(np.asarray(orc[0].W()[0])))           # make sure the refresh really rewrites W
+        eng.refresh()
+        ol = eng.measure()
+        for w, mc in enumerate(orc):
+            Wu, Wd = mc.W()
+            assert np.abs(np.asarray(Wu).imag).max() > 1e-6                 # genuinely complex
+            assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+            assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+            assert abs(ol[w] - mc.getOL()) < TOL * max(1.0, abs(mc.getOL()))
     # explicit rank-1 moves (update_W!, src/MonteCarlo.jl:279-292) against the oracle's complex update
     mv_w, lu, Ku, ld, Kd = [], [], [], [], []
     for w in range(nw):
