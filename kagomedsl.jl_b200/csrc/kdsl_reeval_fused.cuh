@@ -418,7 +418,7 @@ __device__ __noinline__ void fused_update_cols(const FusedArgs FA, double *__res
 //      column sStep[..] of W -- as full, aligned, coalesced segments (thread = site; unit rows of the occupied sites
 //      filled in on the way; every 32-byte sector is written whole, so the L2 never has to fetch one to merge). ----
 template <int NB, int D, bool FIRST>
-__device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *__restrict__ ws, const double *sM, double *stage, int ns) {
+__device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *__restrict__ ws, const double *sM, double *stage, int stage_cap, int ns) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
     const unsigned long long pol = fused_policy_keep();
     (void)pol;
@@ -435,22 +435,23 @@ __device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *_
     double xf[CT][KS];
     bool cv[CT];
     const double *u0p[CT], *u1p[CT];
-    int dsite0[CT], dsite1[CT];                              // staging columns (sites) of my two accumulator columns
+    const int Mp = Cp - Np;
+    // the stage holds 8 rows x Mp unoccupied sites; two of them when they fit (then one barrier per row tile is
+    // enough: the stores of tile rt overlap the DMMAs of tile rt + 1)
+    const int nbuf = stage_cap >= 16 * Mp ? 2 : 1;
 #pragma unroll
     for (int c = 0; c < CT; c++) {
         cv[c] = warp * CT + c < nct;
         const int ct = cv[c] ? t0 + c : t_lo;
 #pragma unroll
         for (int s = 0; s < KS; s++) xf[c][s] = cv[c] ? L.sX[(((ct * KS) + s) << 5) + lane] : 0.0;
-        const int col = (ct << 3) + 2 * tg;
-        const int s0 = sColSite[col], s1 = sColSite[col + 1];
-        dsite0[c] = (cv[c] && s0 < ns) ? s0 : -1;            // (padding columns of the V part map to rows >= ns of UT)
-        dsite1[c] = (cv[c] && s1 < ns) ? s1 : -1;
         if (FIRST) {
-            u0p[c] = UT + (size_t)s0 * Np + gr;
-            u1p[c] = UT + (size_t)s1 * Np + gr;
+            const int col = (ct << 3) + 2 * tg;
+            u0p[c] = UT + (size_t)sColSite[col] * Np + gr;
+            u1p[c] = UT + (size_t)sColSite[col + 1] * Np + gr;
         }
     }
+    double *dep = stage + gr * Mp + ((t0 - t_lo) << 3) + 2 * tg;   // my two accumulator columns = unoccupied sites u, u + 1
     const double *rp = ws + (size_t)gr * Cp + (t0 << 3) + 2 * tg;
     // the writer side: thread = site
     const bool wv = tid < ns;
@@ -471,19 +472,18 @@ __device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *_
         _Pragma("unroll") for (int s = 0; s < KS; s++) mf[s] = sM[((((rt_) * KS) + s) << 5) + lane];           \
         _Pragma("unroll") for (int s = 0; s < KS; s++)                                                         \
             _Pragma("unroll") for (int c = 0; c < CT; c++) dmma_8x8x4((d_)[c].x, (d_)[c].y, mf[s], xf[c][s]);   \
-        _Pragma("unroll") for (int c = 0; c < CT; c++) {                                                       \
-            if (dsite0[c] >= 0) stage[gr * ns + dsite0[c]] = (d_)[c].x;                                        \
-            if (dsite1[c] >= 0) stage[gr * ns + dsite1[c]] = (d_)[c].y;                                        \
-        }                                                                                                      \
+        const int bo_ = (nbuf == 2 && ((rt_) & 1)) ? 8 * Mp : 0;                                               \
+        _Pragma("unroll") for (int c = 0; c < CT; c++)                                                         \
+            if (cv[c]) *reinterpret_cast<double2 *>(dep + bo_ + c * 8) = (d_)[c];                              \
         __syncthreads();                                                                                       \
         if (wv) {                                                                                              \
             _Pragma("unroll") for (int r = 0; r < 8; r++) {                                                    \
                 const int t = sStep[((rt_) << 3) + r];         /* row (rt*8 + r) of B is column t of W */      \
                 if (t < N)                                     /* (else: identity padding) */                  \
-                    __stcs(W + (size_t)t * ns + tid, info >= 0 ? stage[r * ns + tid] : ((-info - 1 == t) ? 1.0 : 0.0)); \
+                    __stcs(W + (size_t)t * ns + tid, info >= 0 ? stage[bo_ + r * Mp + info] : ((-info - 1 == t) ? 1.0 : 0.0)); \
             }                                                                                                  \
         }                                                                                                      \
-        __syncthreads();                                                                                       \
+        if (nbuf == 1) __syncthreads();                                                                        \
     } while (0)
 #pragma unroll
     for (int i = 0; i < D; i++) FUSED_LD(i, buf[i]);
@@ -693,8 +693,9 @@ k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws
                 } else {
                     // output staging: the idle R - E buffer when it holds 8 columns of W, else the dedicated area
                     double *stage = stage_doubles == 0 ? sMn : L.sStg;
-                    if (first) fused_last_step<NB, 4, true>(FA, ws, sM, stage, S.ns);
-                    else fused_last_step<NB, 4, false>(FA, ws, sM, stage, S.ns);
+                    const int stage_cap = stage_doubles == 0 ? NB * Np : stage_doubles;
+                    if (first) fused_last_step<NB, 4, true>(FA, ws, sM, stage, stage_cap, S.ns);
+                    else fused_last_step<NB, 4, false>(FA, ws, sM, stage, stage_cap, S.ns);
                     FUSED_TICK(6, 0);
                 }
             }
