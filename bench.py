@@ -175,11 +175,16 @@ class ClockSampler:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
+        return self.summarise(list(self.lines), t0, t1, getattr(self, "t_load", 0.0))
+
+    @staticmethod
+    def summarise(lines, t0, t1, t_load):
+        """lines: (arrival time, csv line) pairs -> the `clocks` object of the JSON line"""
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
         def parse(lo, hi):
             sm, mx, pw, reasons = [], [], [], set()
-            for ts, ln in list(self.lines):
+            for ts, ln in lines:
                 if ts < lo or ts > hi:
                     continue
                 f = [x.strip() for x in ln.split(",")]
@@ -201,7 +206,7 @@ class ClockSampler:
         sm, mx, pw, reasons = parse(t0, t1 + 0.06)
         if len(sm) < 3:
             window = "warm-up + timed region (the timed region alone is shorter than three 50 ms samples)"
-            sm, mx, pw, reasons = parse(self.t_load if hasattr(self, "t_load") else 0.0, t1 + 0.06)
+            sm, mx, pw, reasons = parse(t_load, t1 + 0.06)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 

@@ -177,3 +177,19 @@ def test_no_cpu_fallback():
     mc = kd.MC({"n1": 2, "n2": 2, "PBC": (False, False), "N_up": 6, "N_down": 6})
     with pytest.raises(kd.KdslError):
         kd.init_(mc, kd.MCContext({"seed": 1}), {"n1": 2, "n2": 2, "N_up": 6})
+
+
+def test_bench_clock_sampler_window():
+    """bench.py reports only the nvidia-smi samples that fall inside the timed region (and says so when it had to widen)"""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    mk = lambda t, mhz, pcap="Not Active": (t, f"{mhz}, 1965, 600.0, Not Active, Not Active, Not Active, {pcap}\n")
+    lines = [mk(0.0, 210), mk(1.0, 1900), mk(2.0, 1965), mk(2.05, 1950, "Active"), mk(2.1, 1965), mk(2.15, 1965), mk(3.0, 300)]
+    c = bench.ClockSampler.summarise(lines, 2.0, 2.15, 1.0)
+    assert c["samples"] == 4 and c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and c["window"] == "timed region"
+    c = bench.ClockSampler.summarise(lines, 2.12, 2.15, 1.0)          # too short: widened over the warm-up
+    assert c["samples"] == 5 and c["window"].startswith("warm-up")
+    assert bench.ClockSampler.summarise([], 0.0, 1.0, 0.0)["sm_mhz"] is None
