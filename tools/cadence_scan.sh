@@ -1,4 +1,4 @@
-for o in "flush_every=8 flush_threshold=16" "flush_every=8 flush_threshold=20" "flush_every=8 flush_threshold=24" "flush_every=12 flush_threshold=16" "flush_every=12 flush_threshold=20" "flush_every=6 flush_threshold=20" "flush_every=4 flush_threshold=24"; do
+for o in "flush_every=8 flush_threshold=16" "flush_every=4 flush_threshold=20" "flush_every=6 flush_threshold=18" "flush_every=8 flush_threshold=12" "flush_every=10 flush_threshold=14"; do
   args=""; for kv in $o; do args="$args --opt $kv"; done
   echo "== $o"; timeout 200 python tools/quick_bench.py --walkers 4096 --sweeps 864 --therm 432 $args 2>&1 | python -c "
 import sys,json
