@@ -189,7 +189,7 @@ int launch_update(kdsl_handle h, int parity) {
     int per_sm = h->update_ctas_per_sm > 0 ? h->update_ctas_per_sm : 4;
     Span sp(h, KDSL_T_UPDATE);
     if (h->cplx) {
-        k_update_c<256><<<h->num_sms * per_sm, 256, (size_t)S.ns * 2 * sizeof(double), h->stream>>>(S, parity, tiles_up, tiles_dn, CH);
+        k_update_c<256><<<h->num_sms * per_sm, 256, (size_t)(S.ns + CH) * 2 * sizeof(double), h->stream>>>(S, parity, tiles_up, tiles_dn, CH);
         CK(cudaGetLastError());
         return KDSL_OK;
     }

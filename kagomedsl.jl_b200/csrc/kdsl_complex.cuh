@@ -198,9 +198,10 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_update_c(DevState S, int parity, int tiles_up, int tiles_dn, int CH) {
     extern __shared__ double smem_c[];
-    cplx *s_col = reinterpret_cast<cplx *>(smem_c);
+    cplx *s_col = reinterpret_cast<cplx *>(smem_c);            // [ns] the staged column, then [CH] the scaled row entries
     const int tid = threadIdx.x;
     const int ns = S.ns;
+    cplx *s_trow = s_col + ns;
     const int n_acc = S.cnt[parity];
     const int tpw = tiles_up + tiles_dn;
     const long long total = (long long)n_acc * tpw;
@@ -221,14 +222,27 @@ k_update_c(DevState S, int parity, int tiles_up, int tiles_dn, int CH) {
         const int j0 = tile * CH, jn = min(CH, N - j0);
         __syncthreads();
         for (int x = tid; x < ns; x += THREADS) s_col[x] = col[x];
+        for (int x = tid; x < jn; x += THREADS) s_trow[x] = trow[j0 + x];
         __syncthreads();
-        for (int jj = 0; jj < jn; jj++) {
-            const cplx tj = trow[j0 + jj];
-            cplx *c = W + (size_t)(j0 + jj) * ns;
-            for (int x = tid; x < ns; x += THREADS) {
-                cplx v = ldg_stream(c + x);
-                v = c_fma(s_col[x], tj, v);
-                stg_stream(c + x, v);
+        // the slab of jn columns is contiguous: four 16-byte elements per thread in flight (one element per thread and
+        // column left the loads of a column waiting on the stores of the previous one: 4.4 TB/s)
+        cplx *base = W + (size_t)j0 * ns;
+        const int n_el = jn * ns;
+        for (int q = tid; q < n_el; q += THREADS * 4) {
+            cplx v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = q + u * THREADS;
+                if (idx < n_el) v[u] = ldg_stream(base + idx);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = q + u * THREADS;
+                if (idx < n_el) {
+                    const int jq = idx / ns, xq = idx - jq * ns;
+                    v[u] = c_fma(s_col[xq], s_trow[jq], v[u]);
+                    stg_stream(base + idx, v[u]);
+                }
             }
         }
     }
