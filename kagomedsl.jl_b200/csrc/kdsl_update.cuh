@@ -59,26 +59,22 @@ k_update_ldg(DevState S, int parity, int tiles_up, int tiles_dn, int CH) {
 
         double2 *base = reinterpret_cast<double2 *>(W + (size_t)j0 * ns);
         const int n2 = jn * half;
-        // (j, p) = (idx / half, idx % half), advanced incrementally
-        int j = tid / half, p = tid - j * half;
-        const int dj = THREADS / half, dp = THREADS - dj * half;
+        // the slab of jn columns is contiguous: UNROLL 16-byte elements per thread in flight, all loads of a trip
+        // issued before its first store
         for (int q = tid; q < n2; q += THREADS * UNROLL) {
             double2 v[UNROLL];
-            int jj[UNROLL], pp[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                jj[u] = j; pp[u] = p;
                 const int idx = q + u * THREADS;
                 if (idx < n2) v[u] = ldg_stream(base + idx);
-                j += dj; p += dp;
-                if (p >= half) { p -= half; j += 1; }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 const int idx = q + u * THREADS;
                 if (idx < n2) {
-                    const double2 c = reinterpret_cast<const double2 *>(s_col)[pp[u]];
-                    const double tj = s_trow[jj[u]];
+                    const int jq = idx / half, pq = idx - jq * half;
+                    const double2 c = reinterpret_cast<const double2 *>(s_col)[pq];
+                    const double tj = s_trow[jq];
                     v[u].x = fma(c.x, tj, v[u].x);            // A[i,j] += x[i] * (alpha*y[j])
                     v[u].y = fma(c.y, tj, v[u].y);
                     stg_stream(base + idx, v[u]);
