@@ -403,7 +403,9 @@ def run_ours(args):
     r1 = t1["moves"] * B_acc / (t1["ms"] * 1e-3) / 1e9 if t1["ms"] > 0 else 0.0
     roofline_rank1 = {"bound": "hbm", "kernel": "k_update_ldg (immediate rank-1 update, one move per walker, timed alone)",
                       "achieved": r1, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": r1 / peak,
-                      "moves_per_launch": t1["moves"] / max(t1["launches"], 1), "algorithmic_bytes_per_move": B_acc}
+                      "moves_per_launch": t1["moves"] / max(t1["launches"], 1), "algorithmic_bytes_per_move": B_acc,
+                      "note": "peak = the driver's measured COPY bandwidth (two address streams); this kernel is an in-place "
+                              "read-modify-write over one stream and can slightly exceed it (ncu launch list: profiles/r1i_launches_summary.txt)"}
     eng.set_option("update_variant", 2)
 
     cpu = None
