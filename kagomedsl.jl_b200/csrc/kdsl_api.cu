@@ -306,11 +306,11 @@ int launch_refresh(kdsl_handle h, const int *list) {
         }
         {
             Span sp(h, KDSL_T_REFRESH_GEMM);
-            k_unembed_c<<<dim3(S.nw, 2), 256, cs * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs);
+            k_unembed_c<<<dim3(S.nw, 2), 256, cs * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs, h->urow, S.ns);
             CK(cudaGetLastError());
             constexpr int BM = 64, BN = 32;
             const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
-            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status);
+            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status, h->urow, S.ns);
             CK(cudaGetLastError());
             h->t_launch[KDSL_T_REFRESH_GEMM] += 1;
         }

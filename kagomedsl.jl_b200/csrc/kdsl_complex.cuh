@@ -396,7 +396,8 @@ k_gather_tilde_emb_c(DevState S, const int *__restrict__ list, double *__restric
 __global__ void __launch_bounds__(256)
 k_unembed_c(DevState S, const int *__restrict__ list, const double *__restrict__ E_up, const double *__restrict__ E_dn,
             double *__restrict__ X_up, double *__restrict__ X_dn, const int *__restrict__ status,
-            const int *__restrict__ colsrc_base, int Ne_up, int Ne_dn, int cs_stride) {
+            const int *__restrict__ colsrc_base, int Ne_up, int Ne_dn, int cs_stride,
+            int *__restrict__ urow_base, int urow_stride) {
     extern __shared__ int s_row_of_step[];
     const int b = blockIdx.x, spin = blockIdx.y;
     if (b >= batch_count(S, list)) return;
@@ -412,13 +413,48 @@ k_unembed_c(DevState S, const int *__restrict__ list, const double *__restrict__
         const double *col = E + (size_t)colsrc[j] * Ne;
         X[e] = c_make(col[s_row_of_step[k]], col[s_row_of_step[N + k]]);
     }
+    // ordered list of the sites NOT occupied by this species (the non-trivial rows of W, computed by k_gemm_W_c) and
+    // the unit rows W[R_l, :] = e_l of the occupied ones (written here, never computed)
+    __shared__ int s_wsum_u[8];
+    __shared__ int s_base_u;
+    const int w = list ? list[b] : b;
+    const int ns = S.ns;
+    const int *kap = (spin ? S.kdn : S.kup) + (size_t)w * ns;
+    int *urow = urow_base + ((size_t)2 * b + spin) * urow_stride;
+    cplx *W = cW(spin ? S.W_dn : S.W_up, (size_t)w * ns * N);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base_u = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < ns; s0 += 256) {
+        const int site = s0 + threadIdx.x;
+        const bool un = site < ns && kap[site] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, un);
+        if (lane == 0) s_wsum_u[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base_u;
+        for (int q = 0; q < warp; q++) off += s_wsum_u[q];
+        if (un) urow[off + __popc(m & ((1u << lane) - 1u))] = site;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int q = 0; q < 8; q++) t += s_wsum_u[q];
+            s_base_u += t;
+        }
+        __syncthreads();
+    }
+    for (int site = threadIdx.x; site < ns; site += blockDim.x) {
+        const int l = kap[site];
+        if (l != 0)
+            for (int n = 0; n < N; n++) W[(size_t)n * ns + site] = c_make(l - 1 == n ? 1.0 : 0.0, 0.0);
+    }
 }
 
 // W[w] (ns x N) = U (ns x N) * X_b (N x N), complex, shared-memory tiled FP64 FMA.  grid (tiles_m * tiles_n, nw, 2).
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(256)
 k_gemm_W_c(DevState S, const int *__restrict__ list, const double *__restrict__ X_up,
-           const double *__restrict__ X_dn, const int *__restrict__ status) {
+           const double *__restrict__ X_dn, const int *__restrict__ status,
+           const int *__restrict__ urow_base = nullptr, int urow_stride = 0) {
     __shared__ cplx As[BK][BM];
     __shared__ cplx Bs[BK][BN + 1];
     const int b = blockIdx.y, spin = blockIdx.z;
@@ -426,9 +462,12 @@ k_gemm_W_c(DevState S, const int *__restrict__ list, const double *__restrict__ 
     if (status[2 * b] | status[2 * b + 1]) return;
     const int w = list ? list[b] : b;
     const int ns = S.ns, N = spin ? S.n_dn : S.n_up;
+    // with urow: only the M = ns - N rows on unoccupied sites are computed (row m of the product is site urow[m])
+    const int *urow = urow_base ? urow_base + ((size_t)2 * b + spin) * urow_stride : nullptr;
+    const int Mrows = urow ? ns - N : ns;
     const int tiles_m = (ns + BM - 1) / BM;
     const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
-    if (tn * BN >= N) return;
+    if (tn * BN >= N || tm * BM >= Mrows) return;
     const cplx *U = cW(spin ? S.U_dn : S.U_up, 0);
     const cplx *X = cW(spin ? X_dn : X_up, (size_t)b * N * N);
     cplx *W = cW(spin ? S.W_dn : S.W_up, (size_t)w * ns * N);
@@ -445,7 +484,7 @@ k_gemm_W_c(DevState S, const int *__restrict__ list, const double *__restrict__ 
         for (int e = tid; e < BK * BM; e += 256) {
             const int kk = e / BM, mm = e - kk * BM;
             const int m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < ns && k < N) ? U[(size_t)k * ns + m] : c_make(0.0, 0.0);
+            As[kk][mm] = (m < Mrows && k < N) ? U[(size_t)k * ns + (urow ? urow[m] : m)] : c_make(0.0, 0.0);
         }
         for (int e = tid; e < BK * BN; e += 256) {
             const int nn = e / BK, kk = e - nn * BK;
@@ -474,7 +513,7 @@ k_gemm_W_c(DevState S, const int *__restrict__ list, const double *__restrict__ 
 #pragma unroll
         for (int a = 0; a < TM; a++) {
             const int m = m0 + tx + 16 * a;
-            if (m < ns) W[(size_t)n * ns + m] = acc[a][c];
+            if (m < Mrows) W[(size_t)n * ns + (urow ? urow[m] : m)] = acc[a][c];
         }
     }
 }
