@@ -65,11 +65,15 @@ def test_refresh_imbalanced_filling_and_variants(kd, variant):
     eng.close()
 
 
-def test_update_W_matches_oracle_and_formula(kd):
-    lat, ham = U.problem(4, 3)
+@pytest.mark.parametrize("cols_per_item,N_up", [(8, None), (5, None), (27, None), (7, 20)])
+def test_update_W_matches_oracle_and_formula(kd, cols_per_item, N_up):
+    """rank-1 kernel (flat walk over a slab of `cols_per_item` columns): slabs that do not divide N, a slab larger
+    than N, and imbalanced filling"""
+    lat, ham = U.problem(4, 3, N_up=N_up)
     ns, nw = kd.ns(lat), 5
     rng = np.random.default_rng(5)
     eng = kd.Engine(ham, nw)
+    eng.set_option("update_cols_per_item", cols_per_item)
     ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw)
     eng.set_config(ku, kdn)
     eng.refresh()
@@ -81,6 +85,7 @@ def test_update_W_matches_oracle_and_formula(kd):
     walkers = np.array([3, 0, 4], dtype=np.int32)
     l_up = np.array([1, ham.N_up, 7]); K_up = np.array([ns, 1, 20])
     l_dn = np.array([2, 5, ham.N_down]); K_dn = np.array([1, ns, 9])
+    eng.set_option("update_variant", 0)                                         # the immediate rank-1 kernel
     eng.update_W(walkers, l_up, K_up, l_dn, K_dn)
     for m, w in enumerate(walkers):
         for spin, (W0, l, K) in enumerate(((Wu0[w], l_up[m], K_up[m]), (Wd0[w], l_dn[m], K_dn[m]))):
