@@ -212,15 +212,16 @@ int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_co
 int kdsl_reset_timers(kdsl_handle h);
 
 /* Tunables: "refresh_every" (0 = reference cadence n_occ); "update_variant" (2 = delayed rank-k updates in
- * Woodbury form, default; 1 = delayed updates with explicit factor lists; 0 = the reference's immediate rank-1
- * update streamed per accepted move); "flush_every" / "flush_threshold" (Woodbury mode: sweeps between flush
- * launches / pending updates that make a walker due; sum <= 32); "fuse_sweeps"; "flush_variant";
+ * Woodbury form, default; 0 = the reference's immediate rank-1 update streamed per accepted move);
+ * "flush_every" / "flush_threshold" (Woodbury mode: sweeps between flush launches / pending updates that make a
+ * walker due; sum <= 32 and small enough for the shared memory of the measurement kernel); "fuse_sweeps";
  * "update_ctas_per_sm", "update_cols_per_item" (rank-1 kernel tiling);
  * "inverse_variant": how reevaluateW! (src/MonteCarlo.jl:55-66) is computed -- 0 (default) / 6 = the one-kernel
  * re-evaluation k_reeval_fused when it applies (N <= 256 per species, ns <= 512), else as 5; 5 / 4 = gather +
- * blocked implicit-pivoting inverse (with / without look-ahead) + DMMA product; 3, 2 = older blocked inverses;
- * 1 = simple cross-check kernels.  "inverse_tuning", "gemm_variant", "fused_ctas": developer knobs.
- * KDSL_ERR_INVALID_ARGUMENT if the name is unknown. */
+ * blocked implicit-pivoting inverse (with / without look-ahead) + DMMA product; 1 = simple cross-check kernels.
+ * "inverse_tuning", "gemm_variant", "fused_ctas": developer knobs.  The superseded variants (update_variant 1,
+ * flush_variant 1, inverse_variant 2 / 3, gemm_variant 2 / 3) exist only in a `make DEV=1` build.
+ * KDSL_ERR_INVALID_ARGUMENT if the name is unknown or the value is not available in this build. */
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);
 
 /*
@@ -235,8 +236,39 @@ int kdsl_event_elapsed(kdsl_handle h, int slot_start, int slot_stop, double *ms)
  * W re-evaluation kernels (MEASURED_PEAKS.json holds no FP64 figure). Runs a ~10 ms register-only probe. */
 int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops);
 
-/* Block until all device work of this handle is complete; returns the first deferred error */
+/* Block until all device work of this handle is complete; returns the first deferred error: a CUDA error, or
+ * KDSL_ERR_SINGULAR when a re-evaluation inside kdsl_sweep / kdsl_replay met a singular tilde_U since the last
+ * kdsl_reset_accumulators (the SingularException that the reference re-throws out of sweep!, src/MonteCarlo.jl:596-603).
+ * Such a walker is frozen: it carries KDSL_FLAG_SINGULAR, proposes no further moves and feeds no :OL samples; the other
+ * walkers of the batch are not affected.  kdsl_sweep / kdsl_replay are asynchronous and return KDSL_OK themselves. */
 int kdsl_synchronize(kdsl_handle h);
+
+/*
+ * Multi-GPU: walkers are independent Markov chains, so a job shards them over one handle per GPU and
+ * the ONLY exchange of the path is the sum of the observable accumulators per bin -- what Carlo.jl does across MPI
+ * ranks when it merges the runs' :acc / :OL observables (src/MonteCarlo.jl:548-589, 632).  No W or kappa ever leaves
+ * its GPU.  The reduction is one ncclAllReduce(sum) of the KDSL_N_ACC doubles, enqueued on the engine's stream behind
+ * the device-side reduction over the handle's own walkers.  libnccl.so.2 is opened with dlopen on first use
+ * (environment KDSL_NCCL_LIB overrides the file name); it is not needed for single-GPU use.
+ *
+ *   one process, several GPUs (the Julia host: one handle per device, one thread):
+ *       kdsl_comm_init_all(n, handles)                      ncclCommInitAll over the handles' devices
+ *       kdsl_group_accumulators_allreduce(n, handles, out)  grouped all-reduce; out = global sums
+ *   one process per GPU (MPI-style launchers):
+ *       rank 0: kdsl_comm_unique_id(id); ship the KDSL_COMM_ID_BYTES bytes to the other ranks by any means
+ *       every rank: kdsl_comm_init_rank(h, n_ranks, rank, id)   (collective)
+ *       every rank: kdsl_accumulators_allreduce(h, out)         (collective; without a communicator = kdsl_accumulators)
+ * kdsl_comm_destroy is implied by kdsl_destroy.
+ */
+#define KDSL_COMM_ID_BYTES 128
+int kdsl_comm_version(int *version);                      /* ncclGetVersion of the library that was opened */
+int kdsl_comm_unique_id(uint8_t *id);
+int kdsl_comm_init_rank(kdsl_handle h, int n_ranks, int rank, const uint8_t *id);
+int kdsl_comm_init_all(int n, kdsl_handle *handles);
+int kdsl_comm_info(kdsl_handle h, int *rank, int *n_ranks);  /* rank = -1, n_ranks = 0 without a communicator */
+int kdsl_comm_destroy(kdsl_handle h);
+int kdsl_accumulators_allreduce(kdsl_handle h, double *out);
+int kdsl_group_accumulators_allreduce(int n, kdsl_handle *handles, double *out);
 
 /* Handle geometry: out[0..5] = ns, n_up, n_dn, n_bonds, n_walkers, n_occ (= min(n_up, n_dn),
  * src/MonteCarlo.jl:594) */

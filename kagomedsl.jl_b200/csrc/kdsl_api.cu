@@ -2,6 +2,8 @@
 // extern "C" entry points declared in include/kdsl.h.  sm_100a only; there is no CPU path:
 // every entry point fails with KDSL_ERR_CUDA when no CUDA device is usable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>              // types and prototypes only: libnccl.so.2 is opened with dlopen at kdsl_comm_* time
 
 #include <algorithm>
 #include <cstdarg>
@@ -16,11 +18,13 @@
 #include "kdsl_propose.cuh"
 #include "kdsl_refresh.cuh"
 #include "kdsl_refresh_fast.cuh"
-#include "kdsl_inverse_v3.cuh"
 #include "kdsl_inverse_v4.cuh"
 #include "kdsl_inverse_v5.cuh"
 #include "kdsl_reeval_fused.cuh"
+#ifdef KDSL_DEV_VARIANTS   // superseded kernels kept for A/B measurements: `make DEV=1` (not in the product library)
+#include "kdsl_inverse_v3.cuh"
 #include "kdsl_delayed.cuh"
+#endif
 #include "kdsl_woodbury.cuh"
 #include "kdsl_update.cuh"
 #include "kdsl_complex.cuh"
@@ -76,6 +80,7 @@ struct kdsl_handle_s {
     size_t fused_smem24 = 0, fused_smem16 = 0;   // the same for panel widths 24 (default) and 16
     int fused_stage24 = 0, fused_stage16 = 0;
     int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
+    size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin of this handle's device
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
     double *d_acc8 = nullptr;     // [8]
@@ -88,6 +93,8 @@ struct kdsl_handle_s {
     int parity = 0;
     bool have_config = false, W_valid = false;
     double *X_up = nullptr, *X_dn = nullptr;   // ComplexF64 mode: un-embedded complex inverses [nw][N*N] (re, im)
+    ncclComm_t comm = nullptr;    // NCCL communicator of this handle's rank (kdsl_comm_init_rank / kdsl_comm_init_all)
+    int comm_rank = -1, comm_size = 0;
     bool cplx = false;            // ComplexF64 mode (kdsl_create_c128): W, U, staging and workspace hold (re, im) pairs
     int64_t walker_sweeps = 0;
     // options
@@ -198,6 +205,7 @@ int launch_update(kdsl_handle h, int parity) {
     return KDSL_OK;
 }
 
+#ifdef KDSL_DEV_VARIANTS
 template <int NB, int RPT, int T, int MINB>
 int launch_inverse_blocked(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     const size_t smem = ((size_t)2 * Np * NB + NB * NB + 2 * NB + T / 32) * sizeof(double) +
@@ -218,6 +226,8 @@ int launch_inverse_v3(kdsl_handle h, const int *list, double *A, int spin, int N
     CK(cudaGetLastError());
     return KDSL_OK;
 }
+
+#endif  // KDSL_DEV_VARIANTS
 
 template <int NB, int RPT, int T, int TP, int MINB = 1, int CT = 3>
 int launch_inverse_v4(kdsl_handle h, const int *list, double *A, int spin, int Np) {
@@ -260,6 +270,7 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
         if (Np <= 1024) return launch_inverse_v4<8, 4, 256, 256>(h, list, A, spin, Np);
         return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
     }
+#ifdef KDSL_DEV_VARIANTS
     if (h->inverse_variant == 3) {
         // one CTA per matrix and ONE CTA per SM: 148 x N^2 x 8 B of live matrices stay L2 resident
         if (Np <= 256) return h->inverse_tuning == 1 ? launch_inverse_v3<24, 1, 512>(h, list, A, spin, Np)
@@ -278,6 +289,9 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
     if (Np <= 512) return launch_inverse_blocked<16, 2, 256, 1>(h, list, A, spin, Np);
     if (Np <= 1024) return launch_inverse_blocked<8, 4, 256, 1>(h, list, A, spin, Np);
     return fail(KDSL_ERR_INVALID_ARGUMENT, "N = %d exceeds the supported maximum of 1024 orbitals per species", Np);
+#else
+    return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant %d is a developer variant (build with make DEV=1)", h->inverse_variant);
+#endif
 }
 
 // reevaluateW! for the walkers in `list` (device list with device count cnt[2]) or all (list = null)
@@ -409,6 +423,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
                 fprintf(stderr, "k_gemm_W_dmma: %d CTAs/SM (dynamic smem %zu)\n", nb, smem);
             }
             const int perm_k = (h->inverse_variant == 0 || h->inverse_variant >= 4) ? 1 : 0;
+#ifdef KDSL_DEV_VARIANTS
             const int cs = std::max(h->Np_up, h->Np_dn);
             if (h->gemm_variant == 2 || h->gemm_variant == 3) {   // cp.async pipeline (measured slightly slower than the register-staged kernel)
                 constexpr int ST = 3;
@@ -421,6 +436,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
                     k_gemm_W_cpasync<KT, ST, 2><<<dim3(tiles, S.nw, 2), 288, sm3, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs, h->urow, S.ns, perm_k);
                 }
             } else
+#endif
             k_gemm_W_dmma<KT><<<dim3(tiles, S.nw, 2), 288, smem, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, std::max(h->Np_up, h->Np_dn), h->urow, S.ns, perm_k);
         } else {
             constexpr int BM = 64, BN = 64;
@@ -437,7 +453,6 @@ int launch_flush_wb_kernel(kdsl_handle h, const int *list, int *cptr) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
     const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KPAD * sizeof(double);
-    CK(cudaFuncSetAttribute(k_flush_wb<KPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         Span sp(h, KDSL_T_UPDATE);
         k_flush_wb<KPAD><<<h->num_sms * 2, 288, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
@@ -452,15 +467,6 @@ int launch_flush_wb_kernel(kdsl_handle h, const int *list, int *cptr) {
 // W0 += pending factors for the listed walkers (list = device list with count cnt[4]) or for all walkers
 int launch_flush(kdsl_handle h, bool all) {
     const DevState &S = h->S;
-    const int Nmax = std::max(S.n_up, S.n_dn);
-    const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KDSL_KMAX * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_measure_wb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
     const int *list = all ? nullptr : S.flush_list;
     int *cptr = all ? nullptr : S.cnt + 4;
     if (h->update_variant == 2 && h->flush_variant == 0) {
@@ -471,6 +477,11 @@ int launch_flush(kdsl_handle h, bool all) {
         h->since_flush = 0;
         return KDSL_OK;
     }
+#ifdef KDSL_DEV_VARIANTS
+    const int Nmax = std::max(S.n_up, S.n_dn);
+    const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KDSL_KMAX * sizeof(double);
+    CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_flush<KDSL_KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         Span sp(h, KDSL_T_UPDATE);
         if (h->update_variant == 2) {
@@ -488,6 +499,7 @@ int launch_flush(kdsl_handle h, bool all) {
         k_zero_int<<<1, 1, 0, h->stream>>>(S.cnt + 4);
         CK(cudaGetLastError());
     }
+#endif
     h->since_flush = 0;
     return KDSL_OK;
 }
@@ -531,6 +543,7 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
                 else
                     k_decide_wb<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, (int)g, nullptr, nullptr, nullptr);
                 CK(cudaGetLastError());
+#ifdef KDSL_DEV_VARIANTS
             } else if (delayed) {
                 if (replay)
                     k_decide<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off, h->rp_bond + off,
@@ -542,6 +555,7 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
                     k_build_factors<KDSL_KMAX><<<h->num_sms * 8, 128, 0, h->stream>>>(S, h->parity);
                     h->parity ^= 1;
                 }
+#endif
             } else if (h->cplx) {
                 if (replay)
                     k_propose_c<true><<<pgrid, 256, 0, h->stream>>>(S, h->parity, gate ? 1 : 0, h->rp_r + off,
@@ -576,7 +590,9 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
         if (therm >= 0 && h->sweeps > therm && (h->sweeps % S.n_occ) == 0) {   // :630 (post-increment)
             Span sp(h, KDSL_T_MEASURE);
             if (woodbury) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, nullptr, 1);
+#ifdef KDSL_DEV_VARIANTS
             else if (delayed) k_measure_delayed<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
+#endif
             else if (h->cplx) k_measure_c<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             else k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             CK(cudaGetLastError());
@@ -742,8 +758,10 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;                  // (the buffers are sized for the largest kmax = 32)
     const size_t kal = cplx ? 1 : KDSL_KALLOC;                    // (no delayed updates in complex mode)
     ALLOC(S.facA_up, nw * kal * ns); ALLOC(S.facA_dn, nw * kal * ns);
+#ifdef KDSL_DEV_VARIANTS
     ALLOC(S.facB_up, nw * kal * ((n_up + 7) / 8 * 8)); ALLOC(S.facB_dn, nw * kal * ((n_dn + 7) / 8 * 8));
-    ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw);
+#endif
+    ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw); ALLOC(S.listed, nw);
     ALLOC(S.wbT, 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
     if (cplx) {
         // the refresh workspace holds the real embedding [[X, -Y], [Y, X]] of tilde_U, padded: Np = roundup(2 N, 8)
@@ -808,6 +826,21 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
         CKD(cudaMemcpy(S.rng, st.data(), st.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
     CKD(cudaFuncSetAttribute(k_inverse_gj, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    // Opt-in dynamic shared memory of the Woodbury kernels.  cudaFuncSetAttribute is per device (context), so this is
+    // done for every handle, not once per process; the sizes are validated against the device limit here and in
+    // kdsl_set_option ("flush_every" / "flush_threshold" change kmax).
+    h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+    if (!cplx) {
+        if (measure_wb_smem(S) > h->smem_optin) {
+            kdsl_destroy(h);
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "k_measure_wb needs %zu bytes of shared memory at ns = %d, kmax = %d (device limit %zu)",
+                        measure_wb_smem(S), ns, S.kmax, h->smem_optin);
+        }
+        CKD(cudaFuncSetAttribute(k_measure_wb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        CKD(cudaFuncSetAttribute(k_flush_wb<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        CKD(cudaFuncSetAttribute(k_flush_wb<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        CKD(cudaFuncSetAttribute(k_flush_wb<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    }
 #undef CKD
     *out = h;
     return KDSL_OK;
@@ -833,6 +866,7 @@ int kdsl_destroy(kdsl_handle h) {
     if (!h) return KDSL_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) kdsl_comm_destroy(h);
     for (auto &s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->user_ev) if (e) cudaEventDestroy(e);
@@ -890,6 +924,7 @@ int kdsl_set_config(kdsl_handle h, const int32_t *kup, const int32_t *kdn) {
     CK(cudaMemsetAsync(S.cnt, 0, 8 * sizeof(int), h->stream));
     CK(cudaMemsetAsync(S.flags, 0, (size_t)S.nw * sizeof(int), h->stream));
     CK(cudaMemsetAsync(S.fcnt, 0, (size_t)2 * S.nw * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(S.listed, 0, (size_t)S.nw * sizeof(int), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->parity = 0;
     h->since_flush = 0;
@@ -993,7 +1028,10 @@ int kdsl_measure(kdsl_handle h, double *ol) {
         Span sp(h, KDSL_T_MEASURE);
         if (h->cplx) k_measure_c<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         else if (h->update_variant == 2) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, h->d_tmp_d, 0);
-        else k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+#ifdef KDSL_DEV_VARIANTS
+        else if (h->update_variant == 1) k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+#endif
+        else k_measure<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(ol, h->d_tmp_d, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1023,25 +1061,16 @@ int kdsl_accumulators(kdsl_handle h, double *out, int64_t *acc_per_walker, doubl
     if (rc) return rc;
     if (!out) return fail(KDSL_ERR_INVALID_ARGUMENT, "out is null");
     const DevState &S = h->S;
-    k_reduce_acc<<<1, 1024, 0, h->stream>>>(S, h->d_acc8);
+    k_reduce_acc<<<1, 1024, 0, h->stream>>>(S, h->d_acc8, (double)h->walker_sweeps);
     CK(cudaGetLastError());
     double tmp[8];
-    int cnt3 = 0;
     CK(cudaMemcpyAsync(tmp, h->d_acc8, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&cnt3, S.cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (acc_per_walker)
         CK(cudaMemcpyAsync(acc_per_walker, S.n_acc, (size_t)S.nw * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     if (ol_sum_per_walker)
         CK(cudaMemcpyAsync(ol_sum_per_walker, S.ol_sum, (size_t)S.nw * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    out[KDSL_ACC_WALKER_SWEEPS] = (double)h->walker_sweeps;
-    out[KDSL_ACC_SUM_ACC] = tmp[1];
-    out[KDSL_ACC_SUM_OL] = tmp[2];
-    out[KDSL_ACC_SUM_OL2] = tmp[3];
-    out[KDSL_ACC_N_OL] = tmp[4];
-    out[KDSL_ACC_N_REACH] = tmp[5];
-    out[KDSL_ACC_N_REFRESH] = tmp[6];
-    out[KDSL_ACC_N_SINGULAR] = (double)cnt3;
+    memcpy(out, tmp, sizeof tmp);                       // (k_reduce_acc writes the KDSL_ACC_* order)
     return KDSL_OK;
 }
 
@@ -1194,7 +1223,10 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         if (value < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "refresh_every must be >= 0");
         h->refresh_every = value;
     } else if (n == "update_variant") {
-        if (value < 0 || value > 2) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming), 1 (delayed factor lists) or 2 (delayed, Woodbury form)");
+        if (value < 0 || value > 2) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming) or 2 (delayed, Woodbury form)");
+#ifndef KDSL_DEV_VARIANTS
+        if (value == 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant 1 (delayed factor lists) is a developer variant (build with make DEV=1)");
+#endif
         if (h->have_config && h->W_valid) {
             int rc = use_device(h);
             if (rc) return rc;
@@ -1216,9 +1248,20 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     else if (n == "update_cols_per_item") {
         if (value < 1 || value > 4096) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_cols_per_item out of range");
         h->update_ch = (int)value;
-    } else if (n == "inverse_variant") h->inverse_variant = (int)value;
+    } else if (n == "inverse_variant") {
+#ifndef KDSL_DEV_VARIANTS
+        if (value == 2 || value == 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+#endif
+        if (value < 0 || value > 6) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5 or 6");
+        h->inverse_variant = (int)value;
+    }
     else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;
-    else if (n == "flush_variant") h->flush_variant = (int)value;
+    else if (n == "flush_variant") {
+#ifndef KDSL_DEV_VARIANTS
+        if (value != 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+#endif
+        h->flush_variant = (int)value;
+    }
     else if (n == "flush_every" || n == "flush_threshold") {
         // Woodbury mode only: a walker is flushed at the first flush launch after it reached `flush_threshold`
         // pending updates; launches come every `flush_every` sweeps, so at most threshold + every are ever pending
@@ -1227,6 +1270,13 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         const int kth = n == "flush_threshold" ? (int)value : h->S.kth;
         if (fe < 1 || kth < 1 || fe + kth > KDSL_KALLOC)
             return fail(KDSL_ERR_INVALID_ARGUMENT, "need flush_every >= 1, flush_threshold >= 1 and their sum <= %d", KDSL_KALLOC);
+        {
+            DevState T = h->S;
+            T.kmax = fe + kth;
+            if (measure_wb_smem(T) > h->smem_optin)
+                return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_every + flush_threshold = %d needs %zu bytes of shared memory in k_measure_wb at ns = %d (device limit %zu)",
+                            fe + kth, measure_wb_smem(T), T.ns, h->smem_optin);
+        }
         int rc = use_device(h);
         if (rc) return rc;
         if (h->have_config && h->W_valid) {               // strides change: no update may be pending
@@ -1238,7 +1288,12 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         h->S.kth = kth;
         h->S.kmax = fe + kth;
     }
-    else if (n == "gemm_variant") h->gemm_variant = (int)value;
+    else if (n == "gemm_variant") {
+#ifndef KDSL_DEV_VARIANTS
+        if (value == 2 || value == 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "gemm_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+#endif
+        h->gemm_variant = (int)value;
+    }
     else if (n == "fused_ctas") h->fused_ctas = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
@@ -1266,7 +1321,8 @@ int kdsl_event_elapsed(kdsl_handle h, int a, int b, double *ms) {
     return KDSL_OK;
 }
 
-/* developer hook (not in kdsl.h): cycles of CTA 0 per phase of k_inverse_blocked since the last call */
+#ifdef KDSL_PHASE_TICKS
+/* developer hook (not in kdsl.h): cycles of CTA 0 per phase of the re-evaluation kernels since the last call */
 int kdsl_debug_inverse_phases(kdsl_handle h, long long *out) {
     int rc = use_device(h);
     if (rc) return rc;
@@ -1276,6 +1332,7 @@ int kdsl_debug_inverse_phases(kdsl_handle h, long long *out) {
     CK(cudaMemcpyToSymbol(g_inv_phase_cycles, z, sizeof z));
     return KDSL_OK;
 }
+#endif
 
 int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops) {
     int rc = use_device(h);
@@ -1302,11 +1359,171 @@ int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops) {
     return KDSL_OK;
 }
 
+/* ---- multi-GPU: NCCL sum of the observable accumulators --------------------------------------------
+ * libnccl.so.2 is not a link-time dependency: it is opened on the first kdsl_comm_* call (KDSL_NCCL_LIB overrides
+ * the name), so a host process that already carries an NCCL (e.g. PyTorch's) shares that copy. */
+namespace {
+struct NcclApi {
+    void *dl = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.dl) return KDSL_OK;
+    const char *name = getenv("KDSL_NCCL_LIB");
+    void *dl = dlopen(name && *name ? name : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return fail(KDSL_ERR_CUDA, "cannot open NCCL (%s): %s", name && *name ? name : "libnccl.so.2", dlerror());
+#define KDSL_NCCL_SYM(f)                                                                  \
+    g_nccl.f = reinterpret_cast<decltype(g_nccl.f)>(dlsym(dl, "nccl" #f));                \
+    if (!g_nccl.f) { dlclose(dl); return fail(KDSL_ERR_CUDA, "NCCL symbol nccl" #f " missing"); }
+    KDSL_NCCL_SYM(GetUniqueId) KDSL_NCCL_SYM(CommInitRank) KDSL_NCCL_SYM(CommInitAll) KDSL_NCCL_SYM(CommDestroy)
+    KDSL_NCCL_SYM(AllReduce) KDSL_NCCL_SYM(GroupStart) KDSL_NCCL_SYM(GroupEnd) KDSL_NCCL_SYM(GetErrorString)
+    KDSL_NCCL_SYM(GetVersion)
+#undef KDSL_NCCL_SYM
+    g_nccl.dl = dl;
+    return KDSL_OK;
+}
+}  // namespace
+#define NCK(call)                                                                                          \
+    do {                                                                                                   \
+        ncclResult_t r_ = (call);                                                                          \
+        if (r_ != ncclSuccess)                                                                             \
+            return fail(KDSL_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_));                 \
+    } while (0)
+
+int kdsl_comm_version(int *version) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    if (!version) return fail(KDSL_ERR_INVALID_ARGUMENT, "version is null");
+    NCK(g_nccl.GetVersion(version));
+    return KDSL_OK;
+}
+
+int kdsl_comm_unique_id(uint8_t *id) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    if (!id) return fail(KDSL_ERR_INVALID_ARGUMENT, "id is null");
+    ncclUniqueId u;
+    NCK(g_nccl.GetUniqueId(&u));
+    static_assert(sizeof u == KDSL_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &u, sizeof u);
+    return KDSL_OK;
+}
+
+int kdsl_comm_init_rank(kdsl_handle h, int n_ranks, int rank, const uint8_t *id) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = nccl_load())) return rc;
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad rank / n_ranks / id");
+    if (h->comm) return fail(KDSL_ERR_STATE, "handle already has a communicator");
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NCK(g_nccl.CommInitRank(&h->comm, n_ranks, u, rank));
+    h->comm_rank = rank;
+    h->comm_size = n_ranks;
+    return KDSL_OK;
+}
+
+int kdsl_comm_init_all(int n, kdsl_handle *handles) {
+    if (n < 1 || !handles) return fail(KDSL_ERR_INVALID_ARGUMENT, "need n >= 1 handles");
+    int rc = nccl_load();
+    if (rc) return rc;
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) {
+        if (!handles[i]) return fail(KDSL_ERR_INVALID_ARGUMENT, "handle %d is null", i);
+        if (handles[i]->comm) return fail(KDSL_ERR_STATE, "handle %d already has a communicator", i);
+        devs[i] = handles[i]->device;
+        for (int j = 0; j < i; j++)
+            if (devs[j] == devs[i]) return fail(KDSL_ERR_INVALID_ARGUMENT, "handles %d and %d share device %d (one handle per GPU)", j, i, devs[i]);
+    }
+    std::vector<ncclComm_t> comms(n);
+    NCK(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; i++) {
+        handles[i]->comm = comms[i];
+        handles[i]->comm_rank = i;
+        handles[i]->comm_size = n;
+    }
+    return KDSL_OK;
+}
+
+int kdsl_comm_destroy(kdsl_handle h) {
+    if (!h) return fail(KDSL_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->comm) return KDSL_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+    h->comm_rank = -1;
+    h->comm_size = 0;
+    return KDSL_OK;
+}
+
+int kdsl_comm_info(kdsl_handle h, int *rank, int *n_ranks) {
+    if (!h) return fail(KDSL_ERR_INVALID_ARGUMENT, "null handle");
+    if (rank) *rank = h->comm_rank;
+    if (n_ranks) *n_ranks = h->comm_size;
+    return KDSL_OK;
+}
+
+/* one rank's share of the reduction (enqueue only) */
+static int enqueue_acc_allreduce(kdsl_handle h) {
+    CK(cudaSetDevice(h->device));
+    k_reduce_acc<<<1, 1024, 0, h->stream>>>(h->S, h->d_acc8, (double)h->walker_sweeps);
+    CK(cudaGetLastError());
+    NCK(g_nccl.AllReduce(h->d_acc8, h->d_acc8, KDSL_N_ACC, ncclDouble, ncclSum, h->comm, h->stream));
+    return KDSL_OK;
+}
+
+int kdsl_accumulators_allreduce(kdsl_handle h, double *out) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (!out) return fail(KDSL_ERR_INVALID_ARGUMENT, "out is null");
+    if (!h->comm) return kdsl_accumulators(h, out, nullptr, nullptr);      // a job of one rank
+    if ((rc = enqueue_acc_allreduce(h))) return rc;
+    CK(cudaMemcpyAsync(out, h->d_acc8, KDSL_N_ACC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KDSL_OK;
+}
+
+int kdsl_group_accumulators_allreduce(int n, kdsl_handle *handles, double *out) {
+    if (n < 1 || !handles || !out) return fail(KDSL_ERR_INVALID_ARGUMENT, "need n >= 1 handles and an output vector");
+    for (int i = 0; i < n; i++)
+        if (!handles[i] || !handles[i]->comm || handles[i]->comm_size != n)
+            return fail(KDSL_ERR_STATE, "handle %d is not part of a %d-rank communicator (call kdsl_comm_init_all first)", i, n);
+    NCK(g_nccl.GroupStart());
+    for (int i = 0; i < n; i++) {
+        int rc = enqueue_acc_allreduce(handles[i]);
+        if (rc) { g_nccl.GroupEnd(); return rc; }
+    }
+    NCK(g_nccl.GroupEnd());
+    CK(cudaSetDevice(handles[0]->device));
+    CK(cudaMemcpyAsync(out, handles[0]->d_acc8, KDSL_N_ACC * sizeof(double), cudaMemcpyDeviceToHost, handles[0]->stream));
+    for (int i = 0; i < n; i++) {
+        CK(cudaSetDevice(handles[i]->device));
+        CK(cudaStreamSynchronize(handles[i]->stream));
+    }
+    return KDSL_OK;
+}
+
 int kdsl_synchronize(kdsl_handle h) {
     int rc = use_device(h);
     if (rc) return rc;
+    int n_sing = 0;
+    CK(cudaMemcpyAsync(&n_sing, h->S.cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    if (n_sing > 0)
+        return fail(KDSL_ERR_SINGULAR, "SingularException: tilde_U was singular in %d walker re-evaluation(s) since the last "
+                    "kdsl_reset_accumulators (those walkers are frozen and carry KDSL_FLAG_SINGULAR)", n_sing);
     return KDSL_OK;
 }
 

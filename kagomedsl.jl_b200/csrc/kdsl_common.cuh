@@ -42,6 +42,7 @@ struct DevState {
     double *wbT;                 // [nw][2][kmax*kmax] Woodbury state: T = inv(W0[K_set, L])
     int *wbK, *wbL;              // [nw][2][kmax] displaced particles: label wbL now sits on site wbK
     int *flush_list;             // [nw] walkers that reached kth pending factors (count in cnt[4])
+    int *listed;                 // [nw] 1 while the walker sits in flush_list (a walker is listed at most once)
     int kmax, kth;
 };
 

@@ -44,6 +44,7 @@ k_propose_c(DevState S, int parity, int gate_refresh, const double *__restrict__
     const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= S.nw) return;
+    if (S.flags[w] & 1) return;      // frozen after a singular re-evaluation (see k_decide_wb; KDSL_FLAG_SINGULAR)
     const int ns = S.ns;
     int *kup = S.kup + (size_t)w * ns;
     int *kdn = S.kdn + (size_t)w * ns;
@@ -547,7 +548,7 @@ k_measure_c(DevState S, double *__restrict__ ol_out, int accumulate) {
         const double OL = flips + 0.25 * (double)diag4;
         if (bad) atomicOr(&S.flags[w], KDSL_FLAG_BAD_SITE_DEV);
         if (ol_out) ol_out[w] = OL;
-        if (accumulate) {
+        if (accumulate && !(S.flags[w] & 1)) {
             S.ol_last[w] = OL;
             S.ol_sum[w] += OL;
             S.ol_sq[w] += OL * OL;

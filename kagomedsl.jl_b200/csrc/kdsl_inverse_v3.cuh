@@ -48,7 +48,7 @@ k_inverse_v3(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gr = lane >> 2, tg = lane & 3;
 
-    long long t_phase = clock64();
+    long long t_phase = PHASE_CLOCK();
     for (int k0 = 0; k0 < Np; k0 += NB) {
         const int kw = min(NB, Np - k0);                // multiple of 8
         // ---- 1. panel columns -> shared memory; identity row maps ----

@@ -50,7 +50,7 @@ k_inverse_v4(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
 #pragma unroll
     for (int r = 0; r < RPT; r++) gstep[r] = 0;
 
-    long long t_phase = clock64();
+    long long t_phase = PHASE_CLOCK();
     for (int k0 = 0; k0 < Np; k0 += NB) {
         const int kw = min(NB, Np - k0);                // multiple of 8
         // ---- 1. panel -> registers ----

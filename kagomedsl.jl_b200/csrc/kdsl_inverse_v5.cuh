@@ -260,29 +260,22 @@ k_inverse_v5(DevState S, const int *__restrict__ list, double *__restrict__ A_ba
     if (sIdx[1]) return;                                // singular
     gather_X(0, min(NB, Np));
     __syncthreads();
-    long long t_phase = clock64();
-#define V5_TICK(idx, thr)                                                            \
-    do {                                                                             \
-        if (blockIdx.x == 0 && threadIdx.x == (thr)) {                               \
-            const long long now_ = clock64();                                        \
-            g_inv_phase_cycles[idx] += now_ - t_phase;                               \
-            t_phase = now_;                                                          \
-        }                                                                            \
-    } while (0)
+    long long t_phase = PHASE_CLOCK();
+#define V5_TICK(idx, thr) PHASE_TICK_AT(idx, thr)
     for (int k0 = 0, s = 0; k0 < Np; k0 += NB, s++) {
         const int kw = min(NB, Np - k0);                // multiple of 8
         const int k1 = k0 + kw, kn = min(NB, Np - k1);  // next panel (kn <= 0: none)
         const double *sM = sMb + (size_t)(s & 1) * NB * Np;
         double *sMn = sMb + (size_t)((s + 1) & 1) * NB * Np;
         const int exn = (kw + max(kn, 0)) >> 3;
-        if (blockIdx.x == 0 && tid == 256) t_phase = clock64();
+        PHASE_RESTART(256);
         V5_TICK(4, 0);                                  // (loop overhead)
         if (kn > 0) {
             update_next_panel(sM, k1 >> 3, kn >> 3);
             __syncthreads();
         }
         V5_TICK(0, 0);
-        if (blockIdx.x == 0 && tid == 256) t_phase = clock64();
+        PHASE_RESTART(256);
         if (teamP) {
             if (kn > 0) factor_panel(k1, kn, sMn);
             V5_TICK(1, 0);

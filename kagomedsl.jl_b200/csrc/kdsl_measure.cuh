@@ -44,7 +44,7 @@ k_measure(DevState S, double *__restrict__ ol_out, int accumulate) {
         const double OL = flips + 0.25 * (double)diag4;
         if (bad) atomicOr(&S.flags[w], KDSL_FLAG_BAD_SITE_DEV);
         if (ol_out) ol_out[w] = OL;
-        if (accumulate) {
+        if (accumulate && !(S.flags[w] & 1)) {                  // (a walker frozen by a singular re-evaluation gives no sample)
             S.ol_last[w] = OL;
             S.ol_sum[w] += OL;
             S.ol_sq[w] += OL * OL;
@@ -74,9 +74,10 @@ __global__ void __launch_bounds__(256) k_count_Z(DevState S, int *__restrict__ o
     }
 }
 
-// Device-side reduction of the per-walker accumulators into out[8] (KDSL_ACC_* order, slot 0 is
-// filled by the host).  Single block; deterministic order.
-__global__ void __launch_bounds__(1024) k_reduce_acc(DevState S, double *__restrict__ out) {
+// Device-side reduction of the per-walker accumulators into out[8] (KDSL_ACC_* order; slot 0 = the host's
+// walker-sweep count, slot 7 = the singular counter cnt[3]).  Single block; deterministic order.  The vector is
+// complete on the device so that it can go straight into the NCCL all-reduce of kdsl_accumulators_allreduce.
+__global__ void __launch_bounds__(1024) k_reduce_acc(DevState S, double *__restrict__ out, double walker_sweeps) {
     __shared__ double sh[32][6];
     double a[6] = {0, 0, 0, 0, 0, 0};
     for (int w = threadIdx.x; w < S.nw; w += blockDim.x) {
@@ -97,5 +98,9 @@ __global__ void __launch_bounds__(1024) k_reduce_acc(DevState S, double *__restr
         double s = 0.0;
         for (int q = 0; q < (int)(blockDim.x >> 5); q++) s += sh[q][threadIdx.x];
         out[1 + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 32) {
+        out[0] = walker_sweeps;
+        out[7] = (double)S.cnt[3];
     }
 }

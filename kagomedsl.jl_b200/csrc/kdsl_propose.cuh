@@ -22,6 +22,7 @@ k_propose(DevState S, int parity, int gate_refresh, const double *__restrict__ r
     const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= S.nw) return;
+    if (S.flags[w] & 1) return;      // frozen after a singular re-evaluation (see k_decide_wb; KDSL_FLAG_SINGULAR)
     const int ns = S.ns;
     int *kup = S.kup + (size_t)w * ns;
     int *kdn = S.kdn + (size_t)w * ns;

@@ -650,15 +650,8 @@ k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws
         if (!L.sIdx[1]) {
             fused_gather_X<NB, T, true>(FA, ws, kw0, kw0);
             __syncthreads();
-            long long t_phase = clock64();
-#define FUSED_TICK(idx, thr)                                                         \
-    do {                                                                             \
-        if (blockIdx.x == 0 && threadIdx.x == (thr)) {                               \
-            const long long now_ = clock64();                                        \
-            g_inv_phase_cycles[idx] += now_ - t_phase;                               \
-            t_phase = now_;                                                          \
-        }                                                                            \
-    } while (0)
+            long long t_phase = PHASE_CLOCK();
+#define FUSED_TICK(idx, thr) PHASE_TICK_AT(idx, thr)
             for (int k0 = 0, s = 0; k0 < Np; k0 += NB, s++) {
                 const int kw = min(NB, Np - k0);            // multiple of 8
                 const int k1 = k0 + kw, kn = min(NB, Np - k1);  // next panel (kn <= 0: none)
@@ -666,14 +659,14 @@ k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws
                 const double *sM = L.sMb + (size_t)(s & 1) * NB * Np;
                 double *sMn = L.sMb + (size_t)((s + 1) & 1) * NB * Np;
                 const int ntc = L.ctx->Cp >> 3;
-                if (blockIdx.x == 0 && threadIdx.x == 256) t_phase = clock64();
+                PHASE_RESTART(256);
                 FUSED_TICK(4, 0);                           // (loop overhead)
                 if (kn > 0) {
                     if (first) fused_update_next_panel<NB, true>(FA, ws, sM, k1, kn);
                     else fused_update_next_panel<NB, false>(FA, ws, sM, k1, kn);
                     __syncthreads();
                     FUSED_TICK(0, 0);
-                    if (blockIdx.x == 0 && threadIdx.x == 256) t_phase = clock64();
+                    PHASE_RESTART(256);
                     if (teamP) {
                         if (DBG != 2) pivoted = fused_factor_panel<NB, false>(FA, ws, k1, kn, sMn, pivoted);
                         else if (threadIdx.x < kn) { L.sPivRow[threadIdx.x] = k1 + threadIdx.x; L.sStep[k1 + threadIdx.x] = k1 + threadIdx.x; }

@@ -78,17 +78,28 @@ k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restri
     }
 }
 
-// developer instrumentation: SM cycles spent by CTA 0 in each phase of k_inverse_blocked
+// developer instrumentation (build with -DKDSL_PHASE_TICKS): SM cycles spent by CTA 0 in each phase of the
+// re-evaluation kernels.  Compiled out of the product library.
+#ifdef KDSL_PHASE_TICKS
 __device__ long long g_inv_phase_cycles[8];
-#define PHASE_TICK(idx)                                                  \
+#define PHASE_CLOCK() clock64()
+#define PHASE_TICK_AT(idx, thr)                                          \
     do {                                                                 \
-        if (blockIdx.x == 0 && threadIdx.x == 0) {                       \
+        if (blockIdx.x == 0 && threadIdx.x == (thr)) {                   \
             const long long now_ = clock64();                            \
             g_inv_phase_cycles[idx] += now_ - t_phase;                   \
             t_phase = now_;                                              \
         }                                                                \
     } while (0)
+#define PHASE_RESTART(thr) do { if (blockIdx.x == 0 && threadIdx.x == (thr)) t_phase = clock64(); } while (0)
+#else
+#define PHASE_CLOCK() 0ll
+#define PHASE_TICK_AT(idx, thr) do { (void)t_phase; } while (0)
+#define PHASE_RESTART(thr) do { } while (0)
+#endif
+#define PHASE_TICK(idx) PHASE_TICK_AT(idx, 0)
 
+#ifdef KDSL_DEV_VARIANTS   // first blocked inverse (explicit row exchanges): superseded by k_inverse_v4 / v5 and k_reeval_fused
 template <int NB, int RPT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB)
 k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__ A_base, int spin,
@@ -113,7 +124,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < NB * NB; e += T) sLU[e] = 0.0;
     __syncthreads();
-    long long t_phase = clock64();
+    long long t_phase = PHASE_CLOCK();
 
     for (int k0 = 0; k0 < Np; k0 += NB) {
         const int kw = min(NB, Np - k0);               // multiple of 8
@@ -393,6 +404,7 @@ k_inverse_blocked(DevState S, const int *__restrict__ list, double *__restrict__
     __syncthreads();
     for (int j = tid; j < Np; j += T) colsrc[j] = sC[j];
 }
+#endif  // KDSL_DEV_VARIANTS
 
 // W[w][unoccupied sites, :] = U[unoccupied sites, :] * X,  X[:, j] = R[:, colsrc[j]] (R stored with leading
 // dimension Np; with perm_k the stored rows are permuted as well: X[k, j] = R[rho, colsrc[j]], k = colsrc[rho]); rows of W on occupied sites are the unit vectors e_l (SURVEY 8(a) invariant) and are written by
@@ -429,7 +441,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     double *W = (spin ? S.W_dn : S.W_up) + (size_t)w * ns * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % 3, wn = warp / 3;
-    long long t_phase = clock64();
+    long long t_phase = PHASE_CLOCK();
     if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
     if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
     for (int k = tid; k < 1024 + 32; k += NT) sKp[k] = k < N ? (perm_k ? colsrc[k] : k) : 0;
@@ -518,6 +530,7 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     PHASE_TICK(7);
 }
 
+#ifdef KDSL_DEV_VARIANTS   // superseded kernels: built only with `make DEV=1`, not part of the product library
 // cp.async version of k_gemm_W_dmma (gemm_variant 0): the operands go global -> shared memory directly (LDGSTS, 8 bytes
 // per element with zero fill), STAGES stages deep, so no register staging, one barrier per stage and loads in flight
 // across stages.  Same tiling (72x72 per CTA, 3x3 warps of 24x24), fragment-major shared layout, same epilogue.
@@ -643,3 +656,5 @@ k_gemm_W_cpasync(DevState S, const int *__restrict__ list, const double *__restr
         }
     }
 }
+
+#endif  // KDSL_DEV_VARIANTS

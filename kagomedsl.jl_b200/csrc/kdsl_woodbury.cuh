@@ -193,8 +193,10 @@ __device__ __forceinline__ void decide_sweep_wb(const DevState &S, int w, int la
             dirty_up |= 1u << wb_accept_warp(S, vu, eu, w, 0, K_up, l_up - 1, lane);
             dirty_dn |= 1u << wb_accept_warp(S, vd, ed, w, 1, K_dn, l_dn - 1, lane);
             const int knew = max(vu.k + (eu.j < 0), vd.k + (ed.j < 0)), kold = max(vu.k, vd.k);
-            if (lane == 0 && knew == S.kth && kold < S.kth) {       // due for a flush (listed exactly once)
-                const int fs = atomicAdd(&S.cnt[4], 1);
+            (void)kold;
+            if (lane == 0 && knew >= S.kth && !S.listed[w]) {       // due for a flush: listed at most once (the flag is
+                S.listed[w] = 1;                                    // cleared by k_flush_finish_wb), so the list cannot
+                const int fs = atomicAdd(&S.cnt[4], 1);             // overflow whatever flush_every / flush_threshold are
                 S.flush_list[fs] = w;
             }
         }
@@ -248,6 +250,10 @@ k_decide_wb(DevState S, int gate_refresh, int n_sweeps, const double *__restrict
     const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= S.nw) return;
+    // A walker whose last re-evaluation met a singular tilde_U is frozen: the reference throws SingularException out of
+    // sweep! at that point (src/MonteCarlo.jl:596-603), here the walker stops proposing, keeps KDSL_FLAG_SINGULAR and is
+    // counted in KDSL_ACC_N_SINGULAR (its W / Woodbury state may no longer belong to its kappa).
+    if (S.flags[w] & KDSL_FLAG_SINGULAR_DEV) return;
     Xoshiro g;
     g.s0 = g.s1 = g.s2 = g.s3 = 0ull;
     if (!REPLAY) {
@@ -308,6 +314,7 @@ __device__ __forceinline__ void wb_compute_G_cta(const WbView &v, const double *
     }
 }
 
+#ifdef KDSL_DEV_VARIANTS   // flush_variant 1 (k_flush_prepare + k_flush): superseded by k_flush_wb
 // Materialise the right flush operand of the listed walkers: facB[m] = G[m, :] = -(T Rt)[m, :], so that k_flush's
 // W0 += sum_m W0[:, l_m] (x) facB[m]  applies  W = W0 - C T Rt  (the left operand C is read from W0 itself).
 // One CTA per (list entry, species).
@@ -332,6 +339,8 @@ k_flush_prepare(DevState S, const int *__restrict__ list, const int *__restrict_
         wb_compute_G_cta(v, sT, sK, sL, B, v.N, -1.0, tid, blockDim.x);
     }
 }
+
+#endif  // KDSL_DEV_VARIANTS
 
 // W0 += C G for the listed walkers (C = columns l_m of W0 itself, G = -T Rt built in the kernel): the HBM-bound pass
 // of the delayed update, Woodbury form.  Persistent CTAs (two per SM) fetch work items from a device counter;
@@ -458,7 +467,8 @@ k_flush_finish_wb(DevState S, const int *__restrict__ list, int *count_ptr, int 
         const int w = list ? list[e] : e;
         S.fcnt[(size_t)2 * w] = 0;
         S.fcnt[(size_t)2 * w + 1] = 0;
-    }
+        if (list) S.listed[w] = 0;                          // (flush-all leaves the list alone: its walkers stay listed
+    }                                                       //  until the next listed flush finds them empty)
     __syncthreads();
     if (threadIdx.x == 0) {
         if (count_ptr) { S.upd_moves[1] += (unsigned long long)count; *count_ptr = 0; }
@@ -466,6 +476,7 @@ k_flush_finish_wb(DevState S, const int *__restrict__ list, int *count_ptr, int 
     }
 }
 
+#ifdef KDSL_DEV_VARIANTS
 // after k_flush in Woodbury mode: both species of the listed walkers are up to date
 __global__ void k_flush_done_wb(DevState S, const int *__restrict__ list, int *count_ptr, int count_fixed) {
     const int count = count_ptr ? *count_ptr : count_fixed;
@@ -476,6 +487,8 @@ __global__ void k_flush_done_wb(DevState S, const int *__restrict__ list, int *c
     }
     if (count_ptr && blockIdx.x == 0 && threadIdx.x == 0) S.upd_moves[1] += (unsigned long long)count;
 }
+
+#endif  // KDSL_DEV_VARIANTS
 
 // O_L (reference getOL, src/Hamiltonian.jl:762-778) with Woodbury-form W; one CTA (256 threads) per walker.
 // Phase 1: G_s = T_s Rt_s (k x N) for both species into shared memory; phase 2: threads stride over the bonds,
@@ -539,7 +552,7 @@ k_measure_wb(DevState S, double *__restrict__ ol_out, int accumulate) {
         const double OL = f + 0.25 * (double)d4;
         if (bd) atomicOr(&S.flags[w], 4);
         if (ol_out) ol_out[w] = OL;
-        if (accumulate) {
+        if (accumulate && !(S.flags[w] & KDSL_FLAG_SINGULAR_DEV)) {   // (a frozen walker's W is stale: no sample)
             S.ol_last[w] = OL;
             S.ol_sum[w] += OL;
             S.ol_sq[w] += OL * OL;

@@ -240,6 +240,23 @@ class Engine:
     def reset_accumulators(self):
         check(self._L.kdsl_reset_accumulators(self._h))
 
+    # -- multi-GPU: NCCL sum of the accumulators inside the C ABI ----------------------------
+    def comm_init_rank(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
+        """collective over the ranks of a one-process-per-GPU job (kdsl_comm_init_rank)"""
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        check(self._L.kdsl_comm_init_rank(self._h, int(n_ranks), int(rank), C.cast(buf, C.c_void_p)))
+
+    def comm_info(self):
+        r, n = C.c_int(-1), C.c_int(0)
+        check(self._L.kdsl_comm_info(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def accumulators_allreduce(self) -> np.ndarray:
+        """global sums over every rank's walkers (one ncclAllReduce of KDSL_N_ACC doubles on the engine's stream)"""
+        out = np.zeros(_lib.N_ACC)
+        check(self._L.kdsl_accumulators_allreduce(self._h, _ptr(out)))
+        return out
+
     # -- inspection / test hooks ---------------------------------------------------------
     def get_W(self, walker: int, spin: int) -> np.ndarray:
         N = self.N_dn if spin else self.N_up
@@ -529,10 +546,14 @@ def run_(mc: MC, ctx: MCContext, n_steps: int) -> None:
 def accumulators(mc: MC, reduce_ranks: bool = True) -> Dict[str, float]:
     """Sums of :acc / :OL over all walkers (and, if torch.distributed is initialised, over all
     ranks: the only inter-GPU exchange of the path) plus the derived means."""
-    v = mc._ensure_engine().accumulators().copy()
-    if reduce_ranks:
-        from .dist import allreduce_sum
-        v = allreduce_sum(v, device=mc.engine.device)
+    eng = mc._ensure_engine()
+    if reduce_ranks and eng.comm_info()[1] > 1:
+        v = eng.accumulators_allreduce()                 # NCCL inside the C ABI (dist.init_comm set it up)
+    else:
+        v = eng.accumulators().copy()
+        if reduce_ranks:
+            from .dist import allreduce_sum
+            v = allreduce_sum(v, device=eng.device)
     out = {
         "walker_sweeps": v[_lib.ACC_WALKER_SWEEPS], "sum_acc": v[_lib.ACC_SUM_ACC], "sum_OL": v[_lib.ACC_SUM_OL],
         "sum_OL2": v[_lib.ACC_SUM_OL2], "n_OL": v[_lib.ACC_N_OL], "n_reach": v[_lib.ACC_N_REACH],
@@ -578,5 +599,6 @@ def read_checkpoint_(mc: MC, inp, defer: bool = False) -> None:
     if mc.engine is not None:
         mc.engine.close()
         mc.engine = None
+    mc._acc_seen = mc._ws_seen = 0.0                    # the new engine's accumulators start from zero
     if not defer:
         mc._ensure_engine()

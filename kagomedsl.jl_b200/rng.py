@@ -74,12 +74,16 @@ class Xoshiro:
 
 
 def walker_states(seed: int, n_walkers: int, first_walker: int = 0) -> np.ndarray:
-    """uint64 [n_walkers][4]: walker w's state is the SplitMix64 stream started at
-    seed * (1 + w_global); `first_walker` offsets the global walker index so that
-    ranks of a multi-GPU job get disjoint streams."""
+    """uint64 [n_walkers][4]: walker w's state is four outputs of the SplitMix64 stream started at
+    mix(seed) XOR mix(~w_global), mix = one SplitMix64 output.  Seed and global walker index are hashed
+    JOINTLY: seed 0 is as good as any other, and distinct (seed, walker) pairs do not collide the way the
+    multiplicative rule seed * (1 + w) did ((2, 1) == (4, 0); seed 0 gave every walker the same stream).
+    `first_walker` offsets the global walker index so that ranks of a multi-GPU job get disjoint streams."""
     out = np.zeros((n_walkers, 4), dtype=np.uint64)
+    _, key = splitmix64(int(seed) & _M)
     for w in range(n_walkers):
-        x = (int(seed) * (1 + first_walker + w)) & _M
+        _, wk = splitmix64(~(first_walker + w) & _M)
+        x = key ^ wk
         for q in range(4):
             x, v = splitmix64(x)
             out[w, q] = v

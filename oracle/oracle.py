@@ -240,10 +240,13 @@ class Xoshiro:
 
 
 def seed_states(seed, n_walkers):
-    """per-walker Xoshiro256++ states: SplitMix64 stream started at seed*(1+walker)  """
+    """per-walker Xoshiro256++ states: four SplitMix64 outputs of the stream started at mix(seed) ^ mix(~walker)
+    (mix = one SplitMix64 output); the seeding policy of the product's rng.walker_states, restated"""
+    M = 0xFFFFFFFFFFFFFFFF
     out = np.zeros((n_walkers, 4), dtype=np.uint64)
+    key = lib().ko_splitmix64(C.byref(C.c_uint64(int(seed) & M)))
     for w in range(n_walkers):
-        x = C.c_uint64((int(seed) * (1 + w)) & 0xFFFFFFFFFFFFFFFF)
+        x = C.c_uint64(key ^ lib().ko_splitmix64(C.byref(C.c_uint64(~w & M))))
         for q in range(4):
             out[w, q] = lib().ko_splitmix64(C.byref(x))
     return out
