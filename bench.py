@@ -29,8 +29,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "walker_sweeps_per_sec_432site_piflux_dsl"
 UNIT = "walker-sweeps/s"
+
+
+def metric_name(args):
+    """BASELINE.json's metric, named after the lattice actually run (432 sites = the headline)"""
+    ns = 3 * args.lattice * args.lattice
+    kind = ("zeroflux" if args.flux == "zero" else "piflux") + ("_peierlsB" if args.B != 0.0 else "")
+    return f"walker_sweeps_per_sec_{ns}site_{kind}_dsl"
 
 
 def parse():
@@ -40,6 +46,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lattice", type=int, default=12, help="n1 = n2 (12 -> 432 sites)")
+    ap.add_argument("--flux", default="pi", choices=["pi", "zero"], help="mean-field ansatz: pi-flux DSL or the zero-flux tables of scripts/zero_flux.jl")
+    ap.add_argument("--B", type=float, default=0.0, help="Peierls flux (B != 0 selects the ComplexF64 engine, scripts/LL.jl)")
+    ap.add_argument("--options", default="", help="engine options name=value,... (developer knob)")
+    ap.add_argument("--no-carlo", action="store_true", help="skip the call-per-sweep e2e_carlo legs")
     ap.add_argument("--walkers-per-gpu", type=int, default=4096)
     ap.add_argument("--thermalization", type=int, default=-1, help="untimed sweeps before warm-up (default 10*ns)")
     ap.add_argument("--seed", type=int, default=1234)
@@ -49,16 +59,27 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(n, nw):
-    return f"{n}x{n} DoubleKagome ({3*n*n} sites) pi-flux DSL, PBC, antiPBC=(true,false), half filling, {nw} walkers/GPU"
+def make_config(args, world):
+    """the `config` object of the JSON line: identical for the GPU arm and the --impl reference arm of the same
+    command line (how many walkers each arm actually advanced is in `walkers_total` / `cpu_baseline.sample`)"""
+    n, nw = args.lattice, args.walkers_per_gpu
+    ns = 3 * n * n
+    flux = "zero-flux" if args.flux == "zero" else "pi-flux DSL"
+    return {"workload": f"{n}x{n} DoubleKagome ({ns} sites) {flux}, PBC, antiPBC=(true,false), half filling, B = {args.B:g}; "
+                        f"GPU arm: {nw} walkers per GPU; CPU arm: bounded sample, one walker per host core",
+            "sweeps_per_step": ns // 2, "walkers_per_gpu": nw, "n_gpus": world,
+            "l2": "inputs_exceed_l2 (W working set %.1f GB per GPU)" % (nw * ns * ns * 8 * (2 if args.B != 0.0 else 1) / 1e9)
+                  if nw * ns * ns * 8 > 126e6 else "W working set %.0f MB per GPU is L2 resident; L2 is not flushed (the chain's own state is the input)" % (nw * ns * ns * 8 / 1e6),
+            "rng": "Xoshiro256++ per walker", "refresh": "reference cadence n_occ"}
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle (restated reference algorithm, ComplexF64) on all host cores
+# CPU arm: the oracle (restated reference algorithm, ComplexF64 like the reference) on all host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_walker_sweeps(ham, kup, kdn, seed, sweeps_per_walker, n_threads, dtype="c128"):
-    """every thread advances its own reference walker by `sweeps_per_walker` Carlo steps
-    (thermalization 0, i.e. O_L measured every n_occ sweeps); returns (walker_sweeps, seconds, E/site)"""
+def cpu_chain_rate(ham, kup, kdn, seed, sweeps_per_step, steps, warmup, n_threads, dtype="c128"):
+    """Every thread advances its OWN reference walker through `warmup` + `steps` steps of `sweeps_per_step` Carlo sweeps
+    (thermalization 0, i.e. O_L measured every n_occ sweeps) and times its own `steps` steps: no join between steps,
+    the threads only start together.  Returns (sum over threads of sweeps / own time, mean seconds per step, E/site)."""
     from oracle import oracle as O
     bonds = np.asarray(ham.nn, dtype=np.int32)
     mcs = []
@@ -67,26 +88,44 @@ def cpu_walker_sweeps(ham, kup, kdn, seed, sweeps_per_walker, n_threads, dtype="
         mc.set_kappa(kup, kdn)
         mc.reevaluateW()
         mcs.append((mc, O.Xoshiro.from_seed(seed + 7919 * t), np.zeros(4)))
+    dts = [0.0] * n_threads
+    go = threading.Barrier(n_threads)
+
     def work(t):
         mc, g, st = mcs[t]
-        mc.run(g, sweeps_per_walker, 0, stats=st)
+        go.wait()
+        for _ in range(warmup):
+            mc.run(g, sweeps_per_step, 0)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mc.run(g, sweeps_per_step, 0, stats=st)
+        dts[t] = time.perf_counter() - t0
     threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
-    t0 = time.perf_counter()
     for th in threads:
         th.start()
     for th in threads:
         th.join()
-    dt = time.perf_counter() - t0
+    rate = sum(sweeps_per_step * steps / dt for dt in dts)
     tot = sum(m[2] for m in mcs)
     e = tot[1] / tot[3] / len(kup) if tot[3] else float("nan")
-    return n_threads * sweeps_per_walker, dt, e, mcs
+    return rate, float(np.mean(dts)) / max(steps, 1), e
 
 
-def setup_problem(n):
+def cpu_baseline_sample(ham, kup, kdn, seed, n_occ, seconds, cores, dtype):
+    """bounded sample (about `seconds` of wall time on all cores) of the CPU arm: sized from a two-bin probe"""
+    probe, _, _ = cpu_chain_rate(ham, kup, kdn, seed, n_occ, 2, 0, cores, dtype)
+    bins = int(max(4, round(seconds * probe / cores / n_occ)))
+    rate, spb, e = cpu_chain_rate(ham, kup, kdn, seed, n_occ, bins, 1, cores, dtype)
+    return rate, bins, e
+
+
+def setup_problem(args):
     import kagomedsl.jl_b200 as kd
+    n = args.lattice
     lat = kd.DoubleKagome(1.0, n, n, (True, True), (True, False))
     ns = kd.ns(lat)
-    ham = kd.Hamiltonian(ns // 2, ns // 2, lat)
+    li, lx = (kd.zero_link_in, kd.zero_link_inter) if args.flux == "zero" else (kd.pi_link_in, kd.pi_link_inter)
+    ham = kd.Hamiltonian(ns // 2, ns // 2, lat, link_in=li, link_inter=lx, B=args.B)
     kup, kdn = kd.init_conf_qr(ham, ns, ns // 2)
     return kd, lat, ham, ns, kup, kdn
 
@@ -95,47 +134,31 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kd, lat, ham, ns, kup, kdn = setup_problem(args.lattice)
+    kd, lat, ham, ns, kup, kdn = setup_problem(args)
     n_occ = ns // 2
     cores = os.cpu_count() or 1
     from oracle import oracle as O
     O.build()
-    bonds = np.asarray(ham.nn, dtype=np.int32)
-    bins_per_step = 16         # one reference step: every core advances its walker by 16 bins (16*n_occ sweeps)
-    sweeps = bins_per_step * n_occ
-    mcs = []
-    for t in range(cores):
-        mc = O.MC(bonds, ham.U_up, ham.U_down, "c128")
-        mc.set_kappa(kup, kdn)
-        mc.reevaluateW()
-        mcs.append((mc, O.Xoshiro.from_seed(args.seed + 7919 * t), np.zeros(4)))
-    def one_step():
-        def work(t):
-            mc, g, st = mcs[t]
-            mc.run(g, sweeps, 0, stats=st)
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-    for _ in range(args.warmup):
-        one_step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_step()
-    dt = time.perf_counter() - t0
-    value = cores * sweeps * args.steps / dt
-    tot = sum(m[2] for m in mcs)
+    # one reference step = every core advances its own walker by `bins` bins of n_occ sweeps (sized for ~1 s per step at
+    # 432 sites); the threads never wait for each other between steps
+    bins = max(1, int(round(16 * (432.0 / ns) ** 3)))
+    sweeps = bins * n_occ
+    rate, sec_per_step, e = cpu_chain_rate(ham, kup, kdn, args.seed, sweeps, args.steps, args.warmup, cores, "c128")
+    rate64, _, _ = cpu_chain_rate(ham, kup, kdn, args.seed, sweeps, max(1, args.steps // 4), 1, cores, "f64") if args.B == 0.0 else (None, 0, 0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(args), "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": workload_name(args.lattice, args.walkers_per_gpu),
-                   "note": "CPU restatement (oracle/) of the Julia reference, ComplexF64 W, one walker per host core"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} walkers x {sweeps} sweeps per step x {args.steps} steps"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "E_per_site": tot[1] / tot[3] / ns if tot[3] else None,
+        "config": make_config(args, args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} walkers (one per host core, each thread times its own steps: no join between steps) x "
+                                   f"{sweeps} sweeps per step x {args.steps} steps, ComplexF64 W like the reference",
+                         "value_f64": rate64,
+                         "note": "CPU restatement (oracle/) of the Julia reference: the reference itself cannot run here (no Julia). "
+                                 "No Dict / allocation / dispatch overhead of the Julia code, but no MKL either; value_f64 = the same "
+                                 "chain with real FP64 W (what the GPU arm computes for B = 0)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "E_per_site": e,
     }
     print(json.dumps(line), flush=True)
 
@@ -243,16 +266,34 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    kd, lat, ham, ns, kup, kdn = setup_problem(args.lattice)
+    kd, lat, ham, ns, kup, kdn = setup_problem(args)
     from kagomedsl.jl_b200 import _lib
     n_occ = ns // 2
     nw = args.walkers_per_gpu
     K, W = args.steps, args.warmup
+    cplx = args.B != 0.0
+    li, lx = (kd.zero_link_in, kd.zero_link_inter) if args.flux == "zero" else (kd.pi_link_in, kd.pi_link_inter)
     mc = kd.MC({"n1": args.lattice, "n2": args.lattice, "PBC": (True, True), "antiPBC": (True, False), "N_up": ns // 2,
-                "N_down": ns // 2, "n_walkers": nw, "device": local})
+                "N_down": ns // 2, "n_walkers": nw, "device": local, "link_in": li, "link_inter": lx, "B": args.B})
     # public-API initialisation; walker streams are disjoint across ranks
     mc.load_configuration(kup, kdn, kd.walker_states(args.seed, nw, first_walker=rank * nw))
     eng = mc.engine
+    for kv in filter(None, args.options.split(",")):
+        name, val = kv.split("=")
+        eng.set_option(name.strip(), int(val))
+    if world > 1:
+        # the per-bin reduction of the observable accumulators runs INSIDE libkdsl (ncclAllReduce on the engine's
+        # stream, communicator made by kdsl_comm_init_rank); torch.distributed only carries the 128-byte unique id,
+        # the barriers around the timed region and the max-over-ranks of the device time
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            kd.dist.init_comm(eng)
+            eng.accumulators_allreduce()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     ctx = kd.MCContext({"thermalization": 0, "seed": args.seed})
     therm = args.thermalization if args.thermalization >= 0 else 10 * ns
     therm = (therm // n_occ) * n_occ                    # keep the bin phase aligned
@@ -265,17 +306,24 @@ def run_ours(args):
         sampler.t_load = time.time()                    # from here on the GPU runs the timed workload (warm-up steps)
     for _ in range(W):                                  # warm-up steps through the public API
         kd.run_(mc, ctx, n_occ)
+        eng.accumulators_allreduce()
     eng.synchronize()
     eng.reset_accumulators()
     eng.reset_timers()
     eng.set_profiling(True)                             # CUDA events around every launch on the engine's stream
 
-    # ---- timed region: K steps, device-timed on the launching stream, max over ranks ----
+    # ---- timed region: K steps, device-timed on the launching stream, max over ranks.  One step = one bin:
+    #      n_occ lock-step sweeps + the O_L measurement + the per-bin sum of the accumulators over all ranks ----
     barrier()
     t_w0 = time.time()
+    reduce_ms = 0.0
     eng.event_record(0)
     for _ in range(K):
         kd.run_(mc, ctx, n_occ)
+        eng.event_record(2)
+        acc_global = eng.accumulators_allreduce()        # device reduction + ncclAllReduce (N > 1) + D2H of 8 doubles
+        eng.event_record(3)
+        reduce_ms += eng.event_elapsed_ms(2, 3)
     eng.event_record(1)
     eng.synchronize()
     t_w1 = time.time()
@@ -284,11 +332,12 @@ def run_ours(args):
     clocks = sampler.stop(t_w0, t_w1) if sampler else None
     tm = eng.timers()
     eng.set_profiling(False)
-    res = kd.accumulators(mc)                            # NCCL all-reduce of the observable accumulators
+    res = kd.accumulators(mc)                            # (global sums once more, as a dict)
+    assert abs(res["sum_OL"] - acc_global[_lib.ACC_SUM_OL]) <= 1e-9 * abs(res["sum_OL"])
     total_walkers = nw * world
     value = total_walkers * n_occ * K / (ms * 1e-3)
-    launches = sum(v["launches"] for v in tm.values())
-    B_acc = 16 * ns * ns                                 # bytes to read+write both W matrices of a walker once
+    launches = sum(v["launches"] for v in tm.values()) + K      # + one k_reduce_acc per step
+    B_acc = 16 * ns * ns * (2 if cplx else 1)            # bytes to read+write both W matrices of a walker once
     upd = tm["update"]
     peaks = {}
     try:
@@ -297,77 +346,94 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"
-    # Rooflines.  (1) The HBM-bound W update of the production path: k_flush_wb folds the >= 16 pending rank-1 updates
-    # of a walker into W with ONE read+write pass (delayed Sherman-Morrison, Woodbury form).  Algorithmic bytes per
-    # launch = walkers flushed x 16 ns^2; the reference's immediate update moves 16 ns^2 per ACCEPTED move.
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    n_flush = upd.get("flushes", 0)
-    achieved = n_flush * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else 0.0
+    tkey = lambda k: traffic.get(f"{k}_{ns}", traffic.get(k) if ns == 432 else None)
     moves_total = res["sum_acc"] / world                 # accepted moves on this rank (all folded by flush or refresh)
-    roofline_update = {"bound": "hbm", "kernel": "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)",
-                       "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                       "traffic": traffic.get("k_flush_wb_dram_bytes_per_walker_flush"),
-                       "walkers_flushed_per_launch": n_flush / max(upd["launches"] // 2, 1), "algorithmic_bytes_per_flush": B_acc,
-                       "avg_launch_us": 1e3 * upd["ms"] / max(upd["launches"] // 2, 1),
-                       "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None,
+    woodbury = upd.get("flushes", 0) > 0
+    # Rooflines.  (1) The HBM-bound W update.  Production path: k_flush_wb folds the >= 16 pending rank-1 updates of a
+    # walker into W with ONE read+write pass (delayed Sherman-Morrison, Woodbury form): algorithmic bytes per launch =
+    # walkers flushed x 16 ns^2.  The reference's immediate update (and the ComplexF64 engine's) moves 16 ns^2 (32 ns^2)
+    # per ACCEPTED move.
+    if woodbury:
+        n_units, unit_name = upd["flushes"], "walker flush"
+        kname = "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)"
+        n_launch = max(upd["launches"] // 2, 1)
+    else:
+        n_units, unit_name = upd.get("moves", 0), "accepted move"
+        kname = "k_update_c / k_update_ldg (immediate rank-1 update per accepted move, 128-bit streaming)"
+        n_launch = max(upd["launches"], 1)
+    achieved = n_units * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else 0.0
+    roofline_update = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                       "frac": achieved / peak, "traffic": tkey("k_flush_wb_dram_bytes_per_walker_flush") if woodbury else None,
+                       "units_per_launch": n_units / n_launch, "unit": "GB/s", "algorithmic_bytes_per_unit": B_acc, "unit_name": unit_name,
+                       "avg_launch_us": 1e3 * upd["ms"] / n_launch, "kernel_share_of_step": upd["ms"] / ms if ms > 0 else None,
                        "rank1_equivalent_GBs": moves_total * B_acc / (upd["ms"] * 1e-3) / 1e9 if upd["ms"] > 0 else None,
-                       "note": "traffic is per walker flush (ncu dram bytes / walkers flushed in the captured launch); "
-                               "rank1_equivalent = accepted moves x 16 ns^2 / flush time, the traffic the reference's per-move update would need"}
-    # (2) FP64 tensor-pipe rooflines of the W re-evaluation: batched inverse (2 N^3 per matrix) and W = U X (2 ns N^2)
-    dmma_peak = eng.fp64_dmma_peak_tflops()
+                       "note": "traffic is per unit (ncu dram bytes of the captured launch / units it processed); rank1_equivalent = "
+                               "accepted moves x 16 ns^2 / update time, the traffic the reference's per-move update would need"}
+    # (2) FP64 tensor-pipe rooflines of the W re-evaluation.  Denominator: DMMA rate sustained for >= 1 s, clocks sampled
+    dsampler = ClockSampler(local) if rank == 0 else None
+    t_d0 = time.time()
+    dmma_peak, dmma_burst = eng.fp64_dmma_peak_tflops(1.0)
+    t_d1 = time.time()
+    dclocks = dsampler.stop(t_d0, t_d1) if dsampler else None
     n_refresh = res["n_refresh"] / world
     Nh = ns // 2
-    dsrc = "measured in this run by kdsl_bench_fp64_dmma (MEASURED_PEAKS.json has no FP64 figure)"
+    cmul = 4.0 if cplx else 1.0                          # real flop per complex multiply-add pair
+    dsrc = ("FP64 DMMA rate sustained over 1 s by kdsl_bench_fp64_dmma_sustained in this run (MEASURED_PEAKS.json has no FP64 "
+            "figure); clocks during the probe in dmma_probe")
 
     # algorithmic flop of one walker refresh (both species) = the reference's inverse + full product
-    flop_survey = 2.0 * (2.0 * Nh ** 3 + 2.0 * ns * Nh ** 2)
+    flop_survey = cmul * 2.0 * (2.0 * Nh ** 3 + 2.0 * ns * Nh ** 2)
 
-    def tensor_roofline(kernel, flop_executed, t_ms, launches, traffic_key, flop_algorithmic):
+    def tensor_roofline(kernel, flop_executed, t_ms, n_launch, traffic_key, flop_algorithmic):
         t = t_ms * 1e-3
         ach = n_refresh * flop_algorithmic / t / 1e12 if t > 0 else 0.0
         exe = n_refresh * flop_executed / t / 1e12 if t > 0 else 0.0
-        return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": dmma_peak, "peak_source": dsrc, "unit": "TFLOP/s",
-                "frac": ach / dmma_peak if dmma_peak > 0 else None, "traffic": traffic.get(traffic_key),
-                "algorithmic_flop_per_walker_refresh": flop_algorithmic, "executed_flop_per_walker_refresh": flop_executed,
-                "executed_tflops": exe, "executed_frac": exe / dmma_peak if dmma_peak > 0 else None,
-                "walker_refreshes_per_step": n_refresh / max(K, 1),
-                "avg_launch_us": 1e3 * t_ms / max(launches, 1), "kernel_share_of_step": t_ms / ms if ms > 0 else None}
+        return {"bound": "tensor", "kernel": kernel, "achieved": exe, "peak": dmma_peak, "peak_source": dsrc, "unit": "TFLOP/s",
+                "frac": exe / dmma_peak if dmma_peak > 0 else None,
+                "frac_meaning": "EXECUTED flop / sustained DMMA peak (how busy the tensor pipe is); the contract figure "
+                                "(SURVEY 8(d) algorithmic flop of the reference's inverse + full product) is in achieved_contract / frac_contract",
+                "achieved_contract": ach, "frac_contract": ach / dmma_peak if dmma_peak > 0 else None,
+                "traffic": tkey(traffic_key), "algorithmic_flop_per_walker_refresh": flop_algorithmic,
+                "executed_flop_per_walker_refresh": flop_executed, "walker_refreshes_per_step": n_refresh / max(K, 1),
+                "avg_launch_us": 1e3 * t_ms / max(n_launch, 1), "kernel_share_of_step": t_ms / ms if ms > 0 else None}
 
     fused = tm["refresh_gemm"]["launches"] == 0 and tm["refresh_inverse"]["launches"] > 0
+    cands = [roofline_update]
+    roofline_inverse = roofline_gemm = None
     if fused:
         # k_reeval_fused: Gauss-Jordan on [tilde_U^T | V^T] (N x (N + M), M = ns - N unoccupied sites): step k touches the
-        # N rows of the N - k - 1 + M unfinished columns -> executed flop per matrix = sum_k 2 N (N - k - 1 + M) ~ 3 N^3.
-        # `achieved` follows the contract (SURVEY 8(d) per-walker figure = what the reference computes: 2 (2 N^3 + 2 ns N^2));
-        # `executed_*` is what the kernel really issues (the unit rows and the explicit inverse are never computed).
+        # N rows of the N - k - 1 + M unfinished columns -> executed flop per matrix = sum_k 2 N (N - k - 1 + M) ~ 3 N^3
+        # (the unit rows and the explicit inverse are never computed)
         M_un = ns - Nh
         flop_exec = 2.0 * sum(2.0 * Nh * (Nh - k - 1 + M_un) for k in range(Nh))
-        roofline_refresh = tensor_roofline(
+        roofline_inverse = tensor_roofline(
             "k_reeval_fused (reevaluateW!: blocked Gauss-Jordan on [tilde_U^T | V^T] with look-ahead, FP64 DMMA, writes W directly)",
             flop_exec, tm["refresh_inverse"]["ms"], tm["refresh_inverse"]["launches"] // 2,
             "k_reeval_fused_dram_bytes_per_walker_refresh", flop_survey)
-        roofline_inverse, roofline_gemm = roofline_refresh, None
-        cands = [roofline_refresh, roofline_update]
-    else:
+        cands.append(roofline_inverse)
+    elif tm["refresh_inverse"]["launches"] > 0:
+        Ne = 2 * Nh if cplx else Nh                      # ComplexF64: inverse through the real 2N x 2N embedding
         roofline_inverse = tensor_roofline("k_inverse_v5 / k_inverse_v4 (batched blocked Gauss-Jordan inverse of tilde_U, FP64 DMMA trailing update)",
-                                           2.0 * 2.0 * Nh ** 3, tm["refresh_inverse"]["ms"], 2 * K, "k_inverse_v4_dram_bytes_per_matrix",
-                                           2.0 * 2.0 * Nh ** 3)
+                                           2.0 * 2.0 * Ne ** 3, tm["refresh_inverse"]["ms"], 2 * K, "k_inverse_v4_dram_bytes_per_matrix",
+                                           cmul * 2.0 * 2.0 * Nh ** 3)
         # (the rows of W on occupied sites are unit vectors and are written, not computed: the kernel executes
         #  2 (ns - N) N^2 flops per matrix where the reference's full product has 2 ns N^2)
-        roofline_gemm = tensor_roofline("k_gemm_W_dmma (W = U inv(tilde_U) on the unoccupied rows, FP64 DMMA)",
-                                        2.0 * 2.0 * (ns - Nh) * Nh ** 2, tm["refresh_gemm"]["ms"], 2 * K,
-                                        "k_gemm_W_dmma_dram_bytes_per_matrix", 2.0 * 2.0 * ns * Nh ** 2)
-        cands = [roofline_inverse, roofline_update, roofline_gemm]
+        roofline_gemm = tensor_roofline("k_gemm_W_dmma / k_gemm_W_c (W = U inv(tilde_U) on the unoccupied rows)",
+                                        cmul * 2.0 * 2.0 * (ns - Nh) * Nh ** 2, tm["refresh_gemm"]["ms"], 2 * K,
+                                        "k_gemm_W_dmma_dram_bytes_per_matrix", cmul * 2.0 * 2.0 * ns * Nh ** 2)
+        cands += [roofline_inverse, roofline_gemm]
     # `roofline` = the kernel with the largest share of the timed step
     roofline = max(cands, key=lambda r: r["kernel_share_of_step"] or 0.0)
 
     # ---- e2e: same work through the public API with HOST buffers (replayed proposal stream) ----
     e2e = None
     if not args.no_e2e:
-        Ke = max(1, min(K, 5))
+        Ke = max(1, min(K, 20))
         rng = np.random.default_rng(args.seed + 17 * rank)
         r_host = torch.empty((Ke, n_occ, nw), dtype=torch.float64, pin_memory=True)
         b_host = torch.empty((Ke, n_occ, nw), dtype=torch.int32, pin_memory=True)
@@ -380,18 +446,46 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for k in range(Ke):
-            eng.replay(r_np[k], b_np[k], thermalization=0)  # H2D of this step's proposal stream + 216 sweeps + measure
+            eng.replay(r_np[k], b_np[k], thermalization=0)  # H2D of this step's proposal stream + n_occ sweeps + measure
             ol, n_ol = eng.last_OL()                        # D2H of the step's result
-            acc_vec = eng.accumulators()
+            acc_vec = eng.accumulators_allreduce()          # per-bin sum over all ranks
         barrier()
         dt = allmax(time.perf_counter() - t0)
+        ctx.sweeps = eng.sweeps
         e2e = {"value": total_walkers * n_occ * Ke / dt, "unit": UNIT, "steps": Ke,
                "h2d_bytes_per_step": int(n_occ * nw * (8 + 4)), "d2h_bytes_per_step": int(nw * 16 + 64),
-               "mode": "kdsl_replay: host supplies (r, bond) for every proposal from pinned memory; O_L and counters copied back"}
+               "mode": "kdsl_replay: host supplies (r, bond) for every proposal from pinned memory; O_L, counters and the "
+                       "all-rank accumulator sums copied back every step"}
+
+    # ---- e2e_carlo: the call-per-sweep protocol a Carlo.jl run loop uses (sweep!; ctx.sweeps += 1; measure!), host-timed:
+    #      sweeps_per_call = 1 is the reference's granularity (one kdsl_sweep + one :acc read-back per sweep),
+    #      sweeps_per_call = n_occ lets one Carlo sweep stand for a whole bin ----
+    e2e_carlo = None
+    if not args.no_carlo and not args.no_e2e:
+        e2e_carlo = {}
+        for spc, bins in ((1, 2), (n_occ, 5)):
+            mc.sweeps_per_call = spc
+            cctx = kd.MCContext({"thermalization": 0, "seed": args.seed})
+            cctx.sweeps = eng.sweeps // spc
+            mc.sync_counters()
+            calls = bins * n_occ // spc
+            kd.step_(mc, cctx)                              # untimed first call
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                kd.step_(mc, cctx)
+            eng.synchronize()
+            barrier()
+            dt = allmax(time.perf_counter() - t0)
+            e2e_carlo[f"sweeps_per_call_{spc}"] = {"value": total_walkers * calls * spc / dt, "unit": UNIT, "calls": calls,
+                                                   "us_per_call": 1e6 * dt / calls, "n_OL_recorded": len(cctx.measurements.get("OL", []))}
+        mc.sweeps_per_call = 1
+        ctx.sweeps = eng.sweeps
 
     # ---- the reference-style immediate rank-1 W update (update_W!, src/MonteCarlo.jl:279-292) timed alone:
-    #      every walker applies one move; 16 ns^2 algorithmic bytes per move, W working set >> L2 ----
-    eng.set_option("update_variant", 0)
+    #      every walker applies one move; 16 ns^2 algorithmic bytes per move ----
+    if not cplx:
+        eng.set_option("update_variant", 0)
     eng.reset_timers()
     eng.set_profiling(True)
     wl = np.arange(nw, dtype=np.int32)
@@ -401,38 +495,44 @@ def run_ours(args):
     t1 = eng.timers()["update"]
     eng.set_profiling(False)
     r1 = t1["moves"] * B_acc / (t1["ms"] * 1e-3) / 1e9 if t1["ms"] > 0 else 0.0
-    roofline_rank1 = {"bound": "hbm", "kernel": "k_update_ldg (immediate rank-1 update, one move per walker, timed alone)",
+    roofline_rank1 = {"bound": "hbm", "kernel": "k_update_ldg / k_update_c (immediate rank-1 update, one move per walker, timed alone)",
                       "achieved": r1, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": r1 / peak,
                       "moves_per_launch": t1["moves"] / max(t1["launches"], 1), "algorithmic_bytes_per_move": B_acc,
                       "note": "peak = the driver's measured COPY bandwidth (two address streams); this kernel is an in-place "
-                              "read-modify-write over one stream and can slightly exceed it (ncu launch list: profiles/r1i_launches_summary.txt)"}
-    eng.set_option("update_variant", 2)
+                              "read-modify-write over one stream and can slightly exceed it"}
+    if not cplx:
+        eng.set_option("update_variant", 2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
         cores = os.cpu_count() or 1
-        probe_ws, probe_dt, _, _ = cpu_walker_sweeps(ham, kup, kdn, args.seed, 2 * n_occ, cores)
-        rate = probe_ws / probe_dt
-        sweeps = int(max(4, round(args.cpu_baseline_seconds * rate / cores / n_occ))) * n_occ
-        ws, dt, e_cpu, _ = cpu_walker_sweeps(ham, kup, kdn, args.seed, sweeps, cores)
-        cpu = {"value": ws / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} walkers (one per core) x {sweeps} sweeps, ComplexF64 oracle, {dt:.1f} s", "E_per_site": e_cpu}
+        rate, bins, e_cpu = cpu_baseline_sample(ham, kup, kdn, args.seed, n_occ, args.cpu_baseline_seconds, cores, "c128")
+        rate64 = None
+        if not cplx:
+            rate64, _, _ = cpu_baseline_sample(ham, kup, kdn, args.seed, n_occ, max(2.0, args.cpu_baseline_seconds / 3), cores, "f64")
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} walkers (one per core, each thread times its own run: no join) x {bins} bins of {n_occ} sweeps, ComplexF64 oracle",
+               "value_f64": rate64, "E_per_site": e_cpu}
 
     if rank == 0:
+        cfg = make_config(args, world)
+        cfg.update({"walkers_total": total_walkers, "thermalization_sweeps": therm,
+                    "w_update": ("delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates)"
+                                 if woodbury else "immediate rank-1 update per accepted move"),
+                    "refresh_kernels": "k_reeval_fused (one kernel)" if fused else "gather + inverse + GEMM kernels",
+                    "step": "n_occ sweeps + O_L measurement + per-bin all-rank sum of the accumulators (inside the timed region)"})
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.lattice, nw), "sweeps_per_step": n_occ, "walkers_total": total_walkers,
-                       "l2": "inputs_exceed_l2 (W working set %.1f GB per GPU)" % (nw * ns * ns * 8 / 1e9),
-                       "thermalization_sweeps": therm, "rng": "Xoshiro256++ per walker on device",
-                       "w_update": "delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates); refresh at the reference cadence n_occ",
-                       "refresh": "k_reeval_fused (one kernel)" if fused else "gather + inverse + GEMM kernels"},
+            "dtype": "c128" if cplx else "f64", "data": "synthetic", "config": cfg,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_w_update": roofline_update,
             "roofline_refresh": roofline_inverse, "roofline_refresh_gemm": roofline_gemm,
-            "roofline_rank1_update": roofline_rank1, "e2e": e2e, "cpu_baseline": cpu,
+            "roofline_rank1_update": roofline_rank1, "e2e": e2e, "e2e_carlo": e2e_carlo, "cpu_baseline": cpu,
+            "reduce": {"us_per_step": 1e3 * reduce_ms / max(K, 1), "what": "k_reduce_acc + ncclAllReduce of 8 doubles (N > 1) + D2H, device-timed, "
+                       "inside every timed step", "nccl_ranks": world},
+            "dmma_probe": {"sustained_tflops": dmma_peak, "burst_tflops": dmma_burst, "seconds": 1.0, "clocks": dclocks},
             "observables": {"E_per_site": res["energy"], "acc": res["acc"], "n_OL": res["n_OL"], "n_singular": res["n_singular"]},
             "kernel_ms": {k: round(v["ms"], 3) for k, v in tm.items()},
         }

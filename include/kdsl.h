@@ -235,6 +235,9 @@ int kdsl_event_elapsed(kdsl_handle h, int slot_start, int slot_stop, double *ms)
 /* Measured FP64 tensor-pipe (DMMA m8n8k4) peak of this device in TFLOP/s: the roofline denominator of the
  * W re-evaluation kernels (MEASURED_PEAKS.json holds no FP64 figure). Runs a ~10 ms register-only probe. */
 int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops);
+/* The same probe launched back to back for `seconds` (0..30) of device time: *sustained = total flop / total time
+ * (the figure to use for a kernel timed inside a long step), *burst = the best single ~10 ms launch; either may be NULL. */
+int kdsl_bench_fp64_dmma_sustained(kdsl_handle h, double seconds, double *sustained, double *burst);
 
 /* Block until all device work of this handle is complete; returns the first deferred error: a CUDA error, or
  * KDSL_ERR_SINGULAR when a re-evaluation inside kdsl_sweep / kdsl_replay met a singular tilde_U since the last

@@ -1334,29 +1334,45 @@ int kdsl_debug_inverse_phases(kdsl_handle h, long long *out) {
 }
 #endif
 
-int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops) {
+int kdsl_bench_fp64_dmma_sustained(kdsl_handle h, double seconds, double *sustained, double *burst) {
     int rc = use_device(h);
     if (rc) return rc;
-    if (!tflops) return fail(KDSL_ERR_INVALID_ARGUMENT, "tflops is null");
+    if (!sustained && !burst) return fail(KDSL_ERR_INVALID_ARGUMENT, "no output");
+    if (!(seconds >= 0.0) || seconds > 30.0) return fail(KDSL_ERR_INVALID_ARGUMENT, "seconds must be in [0, 30]");
     const int iters = 4096, grid = h->num_sms * 8;
-    cudaEvent_t a, b;
+    const double flops = (double)grid * 8 /*warps*/ * iters * 8 /*chains*/ * 512.0;   // per launch (~10 ms)
+    cudaEvent_t a, b, c;
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
-    double best = 0.0;
-    for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventCreate(&c));
+    double best = 0.0, total_ms = 0.0;
+    int launches = 0;
+    CK(cudaEventRecord(c, h->stream));
+    // back-to-back launches until `seconds` of device time have passed (at least four): the sustained figure is the
+    // total flop over the total time, the burst figure the best single launch
+    while (launches < 4 || total_ms < seconds * 1e3) {
         CK(cudaEventRecord(a, h->stream));
         k_dmma_peak<<<grid, 256, 0, h->stream>>>(h->d_acc8, iters);
         CK(cudaEventRecord(b, h->stream));
         CK(cudaEventSynchronize(b));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, a, b));
-        const double flops = (double)grid * 8 /*warps*/ * iters * 8 /*chains*/ * 512.0;
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        CK(cudaEventElapsedTime(&ms, c, b));
+        total_ms = ms;
+        launches++;
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    *tflops = best;
+    cudaEventDestroy(c);
+    if (sustained) *sustained = flops * launches / (total_ms * 1e-3) / 1e12;
+    if (burst) *burst = best;
     return KDSL_OK;
+}
+
+int kdsl_bench_fp64_dmma(kdsl_handle h, double *tflops) {
+    if (!tflops) return fail(KDSL_ERR_INVALID_ARGUMENT, "tflops is null");
+    return kdsl_bench_fp64_dmma_sustained(h, 0.0, nullptr, tflops);
 }
 
 /* ---- multi-GPU: NCCL sum of the observable accumulators --------------------------------------------

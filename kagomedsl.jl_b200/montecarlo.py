@@ -309,10 +309,11 @@ class Engine:
     def synchronize(self):
         check(self._L.kdsl_synchronize(self._h))
 
-    def fp64_dmma_peak_tflops(self) -> float:
-        v = C.c_double(0.0)
-        check(self._L.kdsl_bench_fp64_dmma(self._h, C.byref(v)))
-        return v.value
+    def fp64_dmma_peak_tflops(self, seconds: float = 0.0):
+        """(sustained, burst) FP64 DMMA TFLOP/s of this device: the probe kernel launched back to back for `seconds`"""
+        s, b = C.c_double(0.0), C.c_double(0.0)
+        check(self._L.kdsl_bench_fp64_dmma_sustained(self._h, float(seconds), C.byref(s), C.byref(b)))
+        return s.value, b.value
 
     def event_record(self, slot: int):
         check(self._L.kdsl_event_record(self._h, int(slot)))
@@ -377,8 +378,7 @@ class MC(AbstractMC):
 
     def __init__(self, *args):
         self.engine: Optional[Engine] = None
-        self._acc_seen = 0.0
-        self._ws_seen = 0.0
+        self._acc_w_seen = None          # per-walker accepted-move counts already reported as :acc (None: zeros)
         if len(args) == 1:
             params = args[0]
             n1, n2 = params["n1"], params["n2"]
@@ -448,6 +448,11 @@ class MC(AbstractMC):
             self.load_configuration(*pending)
         return self.engine
 
+    def sync_counters(self) -> None:
+        """make the next sweep_ report :acc relative to the engine's CURRENT counters (after sweeps driven through
+        run_ / the engine directly)"""
+        self._acc_w_seen = self._ensure_engine().accumulators(per_walker=True)[1]
+
     def load_configuration(self, kappa_up, kappa_down, rng_states=None) -> None:
         """put configurations on the GPU and (re)compute W = U * inv(tilde_U) for every walker"""
         eng = self._ensure_engine()
@@ -480,25 +485,26 @@ def init_(mc: MC, ctx: MCContext, params: Dict) -> None:
     N_up = params["N_up"]
     states = np.array([[ctx.rng.next_u64() for _ in range(4)] for _ in range(mc.n_walkers)], dtype=np.uint64)
     find_initial_configuration_(mc, nsites, N_up, states)
-    mc._acc_seen = 0.0
-    mc._ws_seen = 0.0
     mc.engine.reset_accumulators()
+    mc._acc_w_seen = None
 
 
 def sweep_(mc: MC, ctx: MCContext) -> None:
-    """`Carlo.sweep!(mc, ctx)` (src/MonteCarlo.jl:538-607): one proposal for every walker (times
-    sweeps_per_call), then the :acc observable as the acceptance fraction of this call."""
+    """`Carlo.sweep!(mc, ctx)` (src/MonteCarlo.jl:538-607): one proposal for every walker (times sweeps_per_call), then
+    the :acc observable (:548-589).  The reference records 0.0 / 1.0 for its one walker; a batch records the VECTOR of
+    the walkers' acceptance fractions over this call (length n_walkers: a Carlo vector observable, one chain per
+    component), a single walker the scalar."""
     eng = mc._ensure_engine()
     k = mc.sweeps_per_call
     eng.sweeps = ctx.sweeps * k
     eng.sweep(k, -1)
-    acc = eng.accumulators()
-    d_acc = acc[_lib.ACC_SUM_ACC] - mc._acc_seen
-    d_ws = acc[_lib.ACC_WALKER_SWEEPS] - mc._ws_seen
-    mc._acc_seen, mc._ws_seen = acc[_lib.ACC_SUM_ACC], acc[_lib.ACC_WALKER_SWEEPS]
+    acc, acc_w, _ = eng.accumulators(per_walker=True)
+    seen = mc._acc_w_seen if mc._acc_w_seen is not None else np.zeros_like(acc_w)
+    d_w = (acc_w - seen) / float(k)
+    mc._acc_w_seen = acc_w
     if acc[_lib.ACC_N_SINGULAR] > 0:
         raise SingularException(_lib.KDSL_ERR_SINGULAR, "lu factorization failed in reevaluateW! (SingularException)")
-    measure_(ctx, "acc", d_acc / d_ws if d_ws > 0 else 0.0)
+    measure_(ctx, "acc", float(d_w[0]) if mc.n_walkers == 1 else d_w)
 
 
 def measure_(*args):
@@ -599,6 +605,6 @@ def read_checkpoint_(mc: MC, inp, defer: bool = False) -> None:
     if mc.engine is not None:
         mc.engine.close()
         mc.engine = None
-    mc._acc_seen = mc._ws_seen = 0.0                    # the new engine's accumulators start from zero
+    mc._acc_w_seen = None                               # the new engine's accumulators start from zero
     if not defer:
         mc._ensure_engine()
