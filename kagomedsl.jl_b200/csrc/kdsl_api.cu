@@ -80,7 +80,7 @@ struct kdsl_handle_s {
     size_t fused_smem24 = 0, fused_smem16 = 0;   // the same for panel widths 24 (default) and 16
     int fused_stage24 = 0, fused_stage16 = 0;
     int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
-    size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin of this handle's device
+    size_t smem_optin = 0;        // largest dynamic shared memory k_measure_wb may use on this handle's device
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
     double *d_acc8 = nullptr;     // [8]
@@ -829,17 +829,26 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     // Opt-in dynamic shared memory of the Woodbury kernels.  cudaFuncSetAttribute is per device (context), so this is
     // done for every handle, not once per process; the sizes are validated against the device limit here and in
     // kdsl_set_option ("flush_every" / "flush_threshold" change kmax).
-    h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     if (!cplx) {
+        // the largest dynamic allocation a kernel may ask for = the device's opt-in limit minus its static shared memory
+        auto optin_dynamic = [&](const void *func, size_t *out) -> cudaError_t {
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaFuncGetAttributes(&fa, func);
+            if (e != cudaSuccess) return e;
+            const size_t lim = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+            if (out) *out = lim;
+            return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim);
+        };
+        CKD(optin_dynamic((const void *)k_measure_wb, &h->smem_optin));
+        CKD(optin_dynamic((const void *)k_flush_wb<20>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_wb<24>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_wb<32>, nullptr));
         if (measure_wb_smem(S) > h->smem_optin) {
+            const size_t need = measure_wb_smem(S), lim = h->smem_optin;
             kdsl_destroy(h);
             return fail(KDSL_ERR_INVALID_ARGUMENT, "k_measure_wb needs %zu bytes of shared memory at ns = %d, kmax = %d (device limit %zu)",
-                        measure_wb_smem(S), ns, S.kmax, h->smem_optin);
+                        need, ns, KDSL_KMAX, lim);
         }
-        CKD(cudaFuncSetAttribute(k_measure_wb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-        CKD(cudaFuncSetAttribute(k_flush_wb<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-        CKD(cudaFuncSetAttribute(k_flush_wb<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-        CKD(cudaFuncSetAttribute(k_flush_wb<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
     }
 #undef CKD
     *out = h;
