@@ -427,6 +427,30 @@ def run_ours(args):
                                         cmul * 2.0 * 2.0 * (ns - Nh) * Nh ** 2, tm["refresh_gemm"]["ms"], 2 * K,
                                         "k_gemm_W_dmma_dram_bytes_per_matrix", cmul * 2.0 * 2.0 * ns * Nh ** 2)
         cands += [roofline_inverse, roofline_gemm]
+    resident = tm["update"]["launches"] == 0 and tm["refresh_inverse"]["launches"] == 0 and tm["propose"]["launches"] > 0
+    if resident:
+        # k_resident (small lattices): the walker lives in shared memory for the whole call, so neither HBM nor the tensor
+        # pipe bounds it ("for ns = 108 the update is SMEM-resident: report it as a fraction of SMEM throughput").
+        # Shared-memory bytes of the arithmetic: an accepted move reads + writes the compact W of both species
+        # (2 x 2 N_up N_dn doubles), a re-evaluation streams N x ns doubles per species and pivot step (read + write,
+        # shrinking tilde_U^T block: ~ N (ns - N/2) on average).
+        t = tm["propose"]["ms"] * 1e-3
+        upd_b = moves_total * 2.0 * 2.0 * Nh * (ns - Nh) * 8.0
+        ref_b = n_refresh * 2.0 * Nh * 2.0 * Nh * (ns - Nh / 2.0) * 8.0
+        smem_peak = 148 * 128 * 1.965                     # GB/s: 128 B/clk/SM at the 1965 MHz the run holds
+        ach = (upd_b + ref_b) / t / 1e9 if t > 0 else 0.0
+        hbm_b = K * nw * 2.0 * (ns * ns * 8.0)            # W of both species loaded and stored once per walker and launch
+        roofline_resident = {
+            "bound": "smem", "kernel": "k_resident (whole call per walker in one persistent kernel: proposals, rank-1 updates, "
+            "re-evaluation and O_L in shared memory)", "achieved": ach, "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak,
+            "peak_source": "148 SMs x 128 B/clk x 1.965 GHz shared-memory bandwidth (nominal)",
+            "note": "latency bound: one walker per CTA, barriers at accepted moves / pivots; the figure counts only the shared-memory "
+                    "bytes of the W update and re-evaluation arithmetic",
+            "hbm_GBs": hbm_b / t / 1e9 if t > 0 else None, "hbm_frac": hbm_b / t / 1e9 / peak if t > 0 else None,
+            "rank1_equivalent_GBs": moves_total * B_acc / t / 1e9 if t > 0 else None, "traffic": None,
+            "avg_launch_us": 1e3 * tm["propose"]["ms"] / max(tm["propose"]["launches"], 1),
+            "kernel_share_of_step": tm["propose"]["ms"] / ms if ms > 0 else None}
+        cands = [roofline_resident]
     # `roofline` = the kernel with the largest share of the timed step
     roofline = max(cands, key=lambda r: r["kernel_share_of_step"] or 0.0)
 
@@ -519,9 +543,10 @@ def run_ours(args):
     if rank == 0:
         cfg = make_config(args, world)
         cfg.update({"walkers_total": total_walkers, "thermalization_sweeps": therm,
-                    "w_update": ("delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates)"
+                    "w_update": ("walker resident in shared memory (k_resident), rank-1 update per accepted move" if resident else
+                                 "delayed rank-k, Woodbury form (flush launch every 8 sweeps for walkers with >= 16 pending updates)"
                                  if woodbury else "immediate rank-1 update per accepted move"),
-                    "refresh_kernels": "k_reeval_fused (one kernel)" if fused else "gather + inverse + GEMM kernels",
+                    "refresh_kernels": "inside k_resident" if resident else "k_reeval_fused (one kernel)" if fused else "gather + inverse + GEMM kernels",
                     "step": "n_occ sweeps + O_L measurement + per-bin all-rank sum of the accumulators (inside the timed region)"})
         line = {
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -26,6 +26,7 @@
 #include "kdsl_delayed.cuh"
 #endif
 #include "kdsl_woodbury.cuh"
+#include "kdsl_resident.cuh"
 #include "kdsl_update.cuh"
 #include "kdsl_complex.cuh"
 
@@ -80,6 +81,9 @@ struct kdsl_handle_s {
     size_t fused_smem24 = 0, fused_smem16 = 0;   // the same for panel widths 24 (default) and 16
     int fused_stage24 = 0, fused_stage16 = 0;
     int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
+    size_t res_smem = 0;          // dynamic shared memory of k_resident (0: a walker does not fit one CTA)
+    int res_ctas_per_sm = 0;      // resident CTAs of k_resident per SM
+    int res_np = 0;               // its template parameter: column passes of 32 (ceil(max(N_up, N_dn) / 32), 1..4)
     size_t smem_optin = 0;        // largest dynamic shared memory k_measure_wb may use on this handle's device
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
@@ -522,8 +526,41 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
     const DevState &S = h->S;
     const int64_t period = h->refresh_every > 0 ? h->refresh_every : S.n_occ;
     const int pgrid = grid_for_warps(S.nw);
-    const bool delayed = h->update_variant >= 1;
+    const bool delayed = h->update_variant == 1 || h->update_variant == 2;
     const bool woodbury = h->update_variant == 2;
+    if (h->update_variant == 3) {
+        // small lattices: the whole call in ONE persistent kernel, every walker resident in shared memory (kdsl_resident.cuh)
+        for (int64_t s = 0; s < n;) {
+            const int64_t g = std::min<int64_t>(n - s, 1 << 30);
+            ResParams P;
+            P.n_sweeps = (int)g; P.sweep0 = h->sweeps; P.period = period; P.therm = therm;
+            P.phase_p = h->sweeps % period; P.phase_m = h->sweeps % S.n_occ;
+            P.rp_r = replay ? h->rp_r + (size_t)s * S.nw : nullptr;
+            P.rp_bond = replay ? h->rp_bond + (size_t)s * S.nw : nullptr;
+            P.rp_pick = (replay && have_pick) ? h->rp_pick + (size_t)s * S.nw : nullptr;
+            P.work_counter = S.cnt + 6;
+            CK(cudaMemsetAsync(S.cnt + 6, 0, sizeof(int), h->stream));
+            const int grid = std::min(S.nw, h->num_sms * h->res_ctas_per_sm);
+            {
+                Span sp(h, KDSL_T_PROPOSE);
+#define KDSL_RES_LAUNCH(NP_)                                                                         \
+    do {                                                                                             \
+        if (replay) k_resident<true, NP_><<<grid, KDSL_RES_THREADS, h->res_smem, h->stream>>>(S, P); \
+        else k_resident<false, NP_><<<grid, KDSL_RES_THREADS, h->res_smem, h->stream>>>(S, P);       \
+    } while (0)
+                if (h->res_np <= 1) KDSL_RES_LAUNCH(1);
+                else if (h->res_np == 2) KDSL_RES_LAUNCH(2);
+                else if (h->res_np == 3) KDSL_RES_LAUNCH(3);
+                else KDSL_RES_LAUNCH(4);
+#undef KDSL_RES_LAUNCH
+                CK(cudaGetLastError());
+            }
+            h->sweeps += g;
+            h->walker_sweeps += g * S.nw;
+            s += g;
+        }
+        return KDSL_OK;
+    }
     for (int64_t s = 0; s < n;) {
         const bool gate = (h->sweeps % period) == 0;            // src/MonteCarlo.jl:595 (pre-increment)
         int64_t g = 1;
@@ -843,6 +880,32 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
         CKD(optin_dynamic((const void *)k_flush_wb<20>, nullptr));
         CKD(optin_dynamic((const void *)k_flush_wb<24>, nullptr));
         CKD(optin_dynamic((const void *)k_flush_wb<32>, nullptr));
+        // small lattices: the walker-resident kernel when at least two CTAs (walkers) share an SM
+        {
+            const size_t need = resident_smem_bytes(ns, n_up, n_dn, n_bonds);
+            const int np = (std::max(n_up, n_dn) + 31) / 32;     // (M_up = N_dn, M_dn = N_up)
+            const void *fn[2] = {nullptr, nullptr};
+            if (np <= 1) { fn[0] = (const void *)k_resident<false, 1>; fn[1] = (const void *)k_resident<true, 1>; }
+            else if (np == 2) { fn[0] = (const void *)k_resident<false, 2>; fn[1] = (const void *)k_resident<true, 2>; }
+            else if (np == 3) { fn[0] = (const void *)k_resident<false, 3>; fn[1] = (const void *)k_resident<true, 3>; }
+            else if (np == 4) { fn[0] = (const void *)k_resident<false, 4>; fn[1] = (const void *)k_resident<true, 4>; }
+            if (fn[0]) {
+                cudaFuncAttributes fa;
+                CKD(cudaFuncGetAttributes(&fa, fn[0]));
+                if (need + fa.sharedSizeBytes <= (size_t)prop.sharedMemPerBlockOptin) {
+                    CKD(cudaFuncSetAttribute(fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                    CKD(cudaFuncSetAttribute(fn[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                    int nb = 0;
+                    CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn[0], KDSL_RES_THREADS, need));
+                    if (nb >= 1) {
+                        h->res_smem = need;
+                        h->res_ctas_per_sm = nb;
+                        h->res_np = np;
+                        if (nb >= 2 && !getenv("KDSL_NO_RESIDENT")) h->update_variant = 3;
+                    }
+                }
+            }
+        }
         if (measure_wb_smem(S) > h->smem_optin) {
             const size_t need = measure_wb_smem(S), lim = h->smem_optin;
             kdsl_destroy(h);
@@ -1037,6 +1100,7 @@ int kdsl_measure(kdsl_handle h, double *ol) {
         Span sp(h, KDSL_T_MEASURE);
         if (h->cplx) k_measure_c<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         else if (h->update_variant == 2) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, h->d_tmp_d, 0);
+        // (update_variant 0 and 3 keep W itself up to date: the plain kernel below)
 #ifdef KDSL_DEV_VARIANTS
         else if (h->update_variant == 1) k_measure_delayed<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
 #endif
@@ -1106,7 +1170,7 @@ int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     if (!out || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / out");
     const int N = spin ? S.n_dn : S.n_up;
     const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N * (h->cplx ? 2 : 1);
-    if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
+    if ((h->update_variant == 1 || h->update_variant == 2) && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyDeviceToHost));
     return KDSL_OK;
@@ -1119,7 +1183,7 @@ int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
     if (!in || walker < 0 || walker >= S.nw || spin < 0 || spin > 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "bad walker / spin / in");
     const int N = spin ? S.n_dn : S.n_up;
     double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N * (h->cplx ? 2 : 1);
-    if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;
+    if ((h->update_variant == 1 || h->update_variant == 2) && (rc = launch_flush(h, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyHostToDevice));
     return KDSL_OK;
@@ -1143,7 +1207,7 @@ int kdsl_update_W(kdsl_handle h, int n_moves, const int32_t *walker, const int32
         mv[m] = walker[m]; mv[n_moves + m] = l_up[m]; mv[2 * (size_t)n_moves + m] = K_up[m];
         mv[3 * (size_t)n_moves + m] = l_dn[m]; mv[4 * (size_t)n_moves + m] = K_dn[m];
     }
-    if (h->update_variant >= 1 && (rc = launch_flush(h, true))) return rc;
+    if ((h->update_variant == 1 || h->update_variant == 2) && (rc = launch_flush(h, true))) return rc;
     int *d_mv = nullptr;
     CK(cudaMalloc(&d_mv, mv.size() * sizeof(int)));
     CK(cudaMemcpyAsync(d_mv, mv.data(), mv.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1232,11 +1296,14 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         if (value < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "refresh_every must be >= 0");
         h->refresh_every = value;
     } else if (n == "update_variant") {
-        if (value < 0 || value > 2) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming) or 2 (delayed, Woodbury form)");
+        if (value < 0 || value > 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant must be 0 (rank-1 streaming), 2 (delayed, Woodbury form) or 3 (walker resident in shared memory)");
+        if (value == 3 && h->res_smem == 0)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant 3 needs a walker's compact state (%zu bytes at ns = %d) in one CTA's shared memory",
+                        resident_smem_bytes(h->S.ns, h->S.n_up, h->S.n_dn, h->S.n_bonds), h->S.ns);
 #ifndef KDSL_DEV_VARIANTS
         if (value == 1) return fail(KDSL_ERR_INVALID_ARGUMENT, "update_variant 1 (delayed factor lists) is a developer variant (build with make DEV=1)");
 #endif
-        if (h->have_config && h->W_valid) {
+        if (h->have_config && h->W_valid && (h->update_variant == 1 || h->update_variant == 2)) {
             int rc = use_device(h);
             if (rc) return rc;
             if ((rc = launch_flush(h, true))) return rc;

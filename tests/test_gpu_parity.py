@@ -103,11 +103,12 @@ def test_update_W_matches_oracle_and_formula(kd, cols_per_item, N_up):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [2, 0])
+@pytest.mark.parametrize("variant", [3, 2, 0])
 @pytest.mark.parametrize("n1,n2,nw,n_sweeps", [(2, 2, 8, 600), (4, 3, 8, 1500), (6, 6, 6, 2500)])
 def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps, variant):
     """replayed (r, bond) sequence: kappa, Z, acceptance counters bit-exact; W within 1e-10.
-    variant 2 = delayed updates in Woodbury form (default), 0 = immediate rank-1 update like the reference"""
+    variant 3 = walker resident in shared memory (k_resident, the default on these small lattices), 2 = delayed updates
+    in Woodbury form (the default on large ones), 0 = immediate rank-1 update like the reference"""
     PBC, anti = ((False, False), (False, False)) if n1 == 2 else ((True, True), (True, False))
     lat, ham = U.problem(n1, n2, PBC, anti)
     ns = kd.ns(lat)
@@ -151,7 +152,7 @@ def test_replay_trajectory_bit_exact(kd, n1, n2, nw, n_sweeps, variant):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [2, 0])
+@pytest.mark.parametrize("variant", [3, 2, 0])
 def test_device_rng_matches_xoshiro_stream(kd, variant):
     """device-drawn random numbers follow Julia's Xoshiro256++ conventions: same
     trajectory and same final generator state as the oracle fed with the same initial states"""
@@ -323,15 +324,17 @@ def _run_chain(kd, ham, ku, kdn, states, n_sweeps, options):
 
 
 @pytest.mark.parametrize("options", [
-    {"fuse_sweeps": 0},
-    {"flush_every": 4},
-    {"flush_every": 3, "flush_threshold": 5},
-    {"flush_every": 16, "flush_threshold": 16},
-    {"flush_every": 8, "flush_threshold": 2},          # threshold below the cadence: a walker is still listed once
+    {"update_variant": 2},
+    {"update_variant": 2, "fuse_sweeps": 0},
+    {"update_variant": 2, "flush_every": 4},
+    {"update_variant": 2, "flush_every": 3, "flush_threshold": 5},
+    {"update_variant": 2, "flush_every": 16, "flush_threshold": 16},
+    {"update_variant": 2, "flush_every": 8, "flush_threshold": 2},   # threshold below the cadence: a walker is still listed once
     {"update_variant": 0},
 ])
 def test_launch_grouping_and_flush_cadence_do_not_change_the_chain(kd, options):
-    """Fusing proposals into one launch, the flush cadence and the flush kernel are scheduling choices: configurations,
+    """The update algorithm (walker resident in shared memory = the default at 108 sites, Woodbury delayed updates,
+    immediate rank-1), fusing proposals into one launch and the flush cadence are scheduling choices: configurations,
     counters, RNG states and O_L sums must be identical to the default path; W agrees to rounding."""
     lat, ham = U.problem(6, 6)
     ns, nw, n_sweeps = kd.ns(lat), 24, 700
@@ -348,8 +351,9 @@ def test_launch_grouping_and_flush_cadence_do_not_change_the_chain(kd, options):
     assert np.allclose(ref[1][2], got[1][2], rtol=1e-11, atol=1e-11)         # O_L sums per walker
     for a, b in zip(ref[3], got[3]):
         assert U.relerr(a, b) < 1e-11
-    if options == {"fuse_sweeps": 0}:                                        # same arithmetic, different launches: bit-identical
-        for a, b in zip(ref[3], got[3]):
+    if options == {"update_variant": 2, "fuse_sweeps": 0}:                   # same arithmetic, different launches: bit-identical
+        ref2 = _run_chain(kd, ham, ku, kdn, states, n_sweeps, {"update_variant": 2})
+        for a, b in zip(ref2[3], got[3]):
             assert np.array_equal(a, b)
 
 
