@@ -25,6 +25,7 @@
 #include "kdsl_common.cuh"
 #include "kdsl_propose.cuh"
 #include "kdsl_refresh.cuh"
+#include <type_traits>
 
 struct ResParams {
     int n_sweeps;                // sweeps of this call
@@ -57,7 +58,7 @@ __device__ __forceinline__ double *res_d(int off) { return reinterpret_cast<doub
 __device__ __forceinline__ short *res_h(int off) { return reinterpret_cast<short *>(res_sm) + off; }
 struct ResSmem {
     int oWc[2], oT, oStg, oRed, oCtrl, oBond;    // in doubles
-    int hKap[2], hSlot[2], hSite[2];             // in shorts
+    int hKap[2], hSlot[2], hSite[2], hAdjOff, hAdjNbr;   // in shorts
     __device__ __forceinline__ ResSmem(int ns, int n_up, int n_dn, int n_bonds) {
         const int Nmax = max(n_up, n_dn);
         int d = 0;
@@ -72,7 +73,12 @@ struct ResSmem {
         hKap[0] = h; h += ns; hKap[1] = h; h += ns;
         hSlot[0] = h; h += ns; hSlot[1] = h; h += ns;
         hSite[0] = h; h += ns - n_up; hSite[1] = h; h += ns - n_dn;
+        hAdjOff = h; h += ns + 1;
+        hAdjNbr = h; h += 2 * n_bonds;
     }
+    // CSR adjacency of the bond graph (the Z_mu update of an accepted move walks the neighbours of two sites)
+    __device__ __forceinline__ short *adj_off() const { return res_h(hAdjOff); }
+    __device__ __forceinline__ short *adj_nbr() const { return res_h(hAdjNbr); }
     __device__ __forceinline__ double *Wc(int sp) const { return res_d(oWc[sp]); }   // compact W: [N][M]
     __device__ __forceinline__ double *T() const { return res_d(oT); }               // [Nmax][Nmax] re-evaluation scratch (tilde_U^T block)
     // staging: update (temp[N], col[M] per species) / Gauss-Jordan (prow, krow [N+M], fcol [N])
@@ -90,7 +96,7 @@ static_assert(sizeof(ResCtrl) <= 32, "ResCtrl must fit its reserved slot");
 __host__ __device__ inline size_t resident_smem_bytes(int ns, int n_up, int n_dn, int n_bonds) {
     const int Nmax = n_up > n_dn ? n_up : n_dn;
     size_t d = (size_t)n_up * (ns - n_up) + (size_t)n_dn * (ns - n_dn) + (size_t)Nmax * Nmax + 2 * ns + Nmax + 8 + 4 + (n_bonds + 1) / 2;
-    size_t s = (size_t)4 * ns + (ns - n_up) + (ns - n_dn);
+    size_t s = (size_t)4 * ns + (ns - n_up) + (ns - n_dn) + (ns + 1) + 2 * (size_t)n_bonds;
     return d * sizeof(double) + ((s * sizeof(short) + 15) & ~(size_t)15);
 }
 
@@ -225,38 +231,48 @@ __device__ __forceinline__ bool res_reevaluate(const DevState &S, const ResSmem 
             pV[t] = cV[t] ? prow[N + lane + 32 * t] : 0.0;
         }
         constexpr int RU = 4;
-        const double *Tk = Tm + k + 1 + lane;                    // column k + 1 + lane of row 0; the multiplier sits at [-1 - lane]
-        for (int i0 = warp; i0 < N; i0 += RU * NWARP) {
+        const bool t1T = k + 1 + 32 < N;                         // (NP <= 2 is the tuned case: a second tilde_U^T pass or not)
+        // body(i0, tail): rows i0 + r NWARP.  Full groups need no row predicate; the one partial group per warp does.
+        auto body = [&](int i0, auto tail_c) {
+            constexpr bool TAIL = decltype(tail_c)::value;
             double f[RU], vT[RU][NP], vV[RU][NP];
-            bool ok[RU];
+            const double *pt[RU];
+            const double *pw[RU];
 #pragma unroll
             for (int r = 0; r < RU; r++) {
                 const int i = i0 + r * NWARP;
-                ok[r] = i < N;
-                const int ic = ok[r] ? i : i0;                   // (a row past the end re-reads row i0; nothing of it is stored)
-                f[r] = Tm[ic * N + k];
+                const int ic = (TAIL && i >= N) ? i0 : i;        // (a row past the end re-reads row i0; nothing of it is stored)
+                pt[r] = Tm + ic * N + k;
+                pw[r] = Wc + ic * M + lane;
+                f[r] = pt[r][0];
 #pragma unroll
                 for (int t = 0; t < NP; t++) {
-                    if (t == 0 || k + 1 + 32 * t < N) vT[r][t] = Tk[ic * N + 32 * t];
-                    vV[r][t] = Wc[ic * M + lane + 32 * t];
+                    if (t == 0 || (t == 1 ? t1T : k + 1 + 32 * t < N)) vT[r][t] = pt[r][1 + lane + 32 * t];
+                    vV[r][t] = pw[r][32 * t];
                 }
             }
 #pragma unroll
             for (int r = 0; r < RU; r++)
 #pragma unroll
                 for (int t = 0; t < NP; t++) {
-                    if (t == 0 || k + 1 + 32 * t < N) vT[r][t] = fma(-f[r], pT[t], vT[r][t]);
+                    if (t == 0 || (t == 1 ? t1T : k + 1 + 32 * t < N)) vT[r][t] = fma(-f[r], pT[t], vT[r][t]);
                     vV[r][t] = fma(-f[r], pV[t], vV[r][t]);
                 }
 #pragma unroll
             for (int r = 0; r < RU; r++) {
-                const int i = i0 + r * NWARP;
+                if (TAIL && i0 + r * NWARP >= N) break;
+                double *qt = const_cast<double *>(pt[r]) + 1 + lane, *qw = const_cast<double *>(pw[r]);
 #pragma unroll
                 for (int t = 0; t < NP; t++) {
-                    if (ok[r] && cT[t]) Tm[i * N + k + 1 + lane + 32 * t] = vT[r][t];
-                    if (ok[r] && cV[t]) Wc[i * M + lane + 32 * t] = vV[r][t];
+                    if (cT[t]) qt[32 * t] = vT[r][t];
+                    if (cV[t]) qw[32 * t] = vV[r][t];
                 }
             }
+        };
+        {
+            int i0 = warp;
+            for (; i0 + (RU - 1) * NWARP < N; i0 += RU * NWARP) body(i0, std::false_type{});
+            if (i0 < N) body(i0, std::true_type{});
         }
         if (warp == (p & (NWARP - 1))) {                         // the pivot row itself (its owner just wrote zeros there)
 #pragma unroll
@@ -336,6 +352,8 @@ k_resident(DevState S, ResParams P) {
     const int ns = S.ns;
     const int Nn[2] = {S.n_up, S.n_dn}, Mm[2] = {ns - S.n_up, ns - S.n_dn};
     for (int b = tid; b < S.n_bonds; b += T) L.bond()[b] = make_short2((short)S.bi[b], (short)S.bj[b]);   // (once per CTA)
+    for (int x = tid; x <= ns; x += T) L.adj_off()[x] = (short)S.adj_off[x];
+    for (int x = tid; x < 2 * S.n_bonds; x += T) L.adj_nbr()[x] = (short)S.adj_nbr[x];
 
     for (;;) {
         __syncthreads();
@@ -447,12 +465,16 @@ k_resident(DevState S, ResParams P) {
                                         const int l = (sp ? l_dn : l_up) - 1, q = sp ? q_dn : q_up;
                                         const double alpha = -1.0 / (sp ? wd : wu);
                                         double *temp = L.stg() + (sp ? S.n_up + Mm[0] : 0), *col = temp + N;
-                                        for (int j = lane; j < N; j += 32) {
-                                            double v = L.Wc(sp)[j * M + q];
-                                            if (j == l) v -= 1.0;
-                                            temp[j] = alpha * v;
+#pragma unroll
+                                        for (int t = 0; t < NP; t++) {
+                                            const int j = lane + 32 * t;
+                                            if (j < N) {
+                                                double v = L.Wc(sp)[j * M + q];
+                                                if (j == l) v -= 1.0;
+                                                temp[j] = alpha * v;
+                                            }
+                                            if (j < M) col[j] = L.Wc(sp)[l * M + j];
                                         }
-                                        for (int u = lane; u < M; u += 32) col[u] = L.Wc(sp)[l * M + u];
                                         if (lane == 0) { L.ctrl()->l[sp] = l; L.ctrl()->q[sp] = q; }
                                     }
                                     ev |= RES_EV_UPDATE;
@@ -462,14 +484,14 @@ k_resident(DevState S, ResParams P) {
                                 const int ui_n = flag == 1 ? 0 : 1, di_n = flag == 1 ? 1 : 0;
                                 const int us_n = flag == 1 ? 1 : 0, ds_n = flag == 1 ? 0 : 1;
                                 int delta = 0;
-                                for (int qq = __ldg(S.adj_off + i) + lane; qq < __ldg(S.adj_off + i + 1); qq += 32) {
-                                    const int n = __ldg(S.adj_nbr + qq);
+                                for (int qq = L.adj_off()[i] + lane; qq < L.adj_off()[i + 1]; qq += 32) {
+                                    const int n = L.adj_nbr()[qq];
                                     if (n == site) continue;
                                     const int un = L.kap(0)[n] != 0, dn = L.kap(1)[n] != 0;
                                     delta += bond_is_anti(ui_n, di_n, un, dn) - bond_is_anti(ui_o, di_o, un, dn);
                                 }
-                                for (int qq = __ldg(S.adj_off + site) + lane; qq < __ldg(S.adj_off + site + 1); qq += 32) {
-                                    const int n = __ldg(S.adj_nbr + qq);
+                                for (int qq = L.adj_off()[site] + lane; qq < L.adj_off()[site + 1]; qq += 32) {
+                                    const int n = L.adj_nbr()[qq];
                                     if (n == i) continue;
                                     const int un = L.kap(0)[n] != 0, dn = L.kap(1)[n] != 0;
                                     delta += bond_is_anti(us_n, ds_n, un, dn) - bond_is_anti(us_o, ds_o, un, dn);
