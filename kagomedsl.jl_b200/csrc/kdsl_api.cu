@@ -26,6 +26,7 @@
 #include "kdsl_delayed.cuh"
 #endif
 #include "kdsl_woodbury.cuh"
+#include "kdsl_flush.cuh"
 #include "kdsl_resident.cuh"
 #include "kdsl_update.cuh"
 #include "kdsl_complex.cuh"
@@ -81,6 +82,8 @@ struct kdsl_handle_s {
     size_t fused_smem24 = 0, fused_smem16 = 0;   // the same for panel widths 24 (default) and 16
     int fused_stage24 = 0, fused_stage16 = 0;
     int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
+    double *Gbuf = nullptr;       // [nw][2][Gstride] flush operands G = -T Rt in DMMA fragment order (k_flush_G -> k_flush_tma; flush_variant 3 only)
+    size_t Gstride = 0;
     size_t res_smem = 0;          // dynamic shared memory of k_resident (0: a walker does not fit one CTA)
     int res_ctas_per_sm = 0;      // resident CTAs of k_resident per SM
     int res_np = 0;               // its template parameter: column passes of 32 (ceil(max(N_up, N_dn) / 32), 1..4)
@@ -105,6 +108,7 @@ struct kdsl_handle_s {
     int64_t refresh_every = 0;
     int update_variant = 2, update_ctas_per_sm = 0, inverse_variant = 0, gemm_variant = 0;
     int since_flush = 0;
+    int flush_dbg = 0;            // developer probe bits of k_flush_tma
     int flush_variant = 0;        // 0: k_flush_wb (persistent, 128-bit), 1: k_flush
     int flush_every = KDSL_FLUSH_EVERY;   // sweeps between flush launches (kmax = kth + flush_every <= 32)
     int fuse_sweeps = 1;          // fuse consecutive proposals into one launch where the loop allows it
@@ -459,7 +463,16 @@ int launch_flush_wb_kernel(kdsl_handle h, const int *list, int *cptr) {
     const size_t smem = (size_t)((Nmax + 7) / 8) * 8 * KPAD * sizeof(double);
     {
         Span sp(h, KDSL_T_UPDATE);
-        k_flush_wb<KPAD><<<h->num_sms * 2, 288, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
+        if (h->flush_variant == 0) {                      // register-pipelined kernel, G built per 216-row item (fastest measured)
+            k_flush_wb<KPAD><<<h->num_sms * 2, 288, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
+        } else {                                          // 3: bulk-async shared-memory ring (k_flush_G + k_flush_tma), see kdsl_flush.cuh
+            k_flush_G<KPAD><<<h->num_sms * 2, 288, smem, h->stream>>>(S, list, cptr, S.nw, h->Gbuf, h->Gstride);
+            CK(cudaGetLastError());
+            const size_t ring3 = ((smem + 127) & ~(size_t)127) + (size_t)4 * 8 * 1728;
+            const int per_sm = 2 * (ring3 + 2048) <= (size_t)227 * 1024 ? 2 : 1;
+            k_flush_tma<KPAD, 4, 3><<<h->num_sms * per_sm, 320, ring3, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, h->Gbuf, h->Gstride, h->flush_dbg);
+            h->t_launch[KDSL_T_UPDATE] += 1;
+        }
         CK(cudaGetLastError());
     }
     k_flush_finish_wb<<<1, 1024, 0, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
@@ -473,7 +486,7 @@ int launch_flush(kdsl_handle h, bool all) {
     const DevState &S = h->S;
     const int *list = all ? nullptr : S.flush_list;
     int *cptr = all ? nullptr : S.cnt + 4;
-    if (h->update_variant == 2 && h->flush_variant == 0) {
+    if (h->update_variant == 2 && (h->flush_variant == 0 || h->flush_variant == 3)) {
         int rc = S.kmax <= 20 ? launch_flush_wb_kernel<20>(h, list, cptr)
                : S.kmax <= 24 ? launch_flush_wb_kernel<24>(h, list, cptr)
                               : launch_flush_wb_kernel<32>(h, list, cptr);
@@ -800,6 +813,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
 #endif
     ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw); ALLOC(S.listed, nw);
     ALLOC(S.wbT, 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
+    h->Gstride = (size_t)((std::max(n_up, n_dn) + 7) / 8 * 8) * KDSL_KALLOC;   // (Gbuf itself is allocated when flush_variant 3 is chosen)
     if (cplx) {
         // the refresh workspace holds the real embedding [[X, -Y], [Y, X]] of tilde_U, padded: Np = roundup(2 N, 8)
         h->Np_up = (2 * n_up + 7) / 8 * 8; h->Np_dn = (2 * n_dn + 7) / 8 * 8;
@@ -880,6 +894,12 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
         CKD(optin_dynamic((const void *)k_flush_wb<20>, nullptr));
         CKD(optin_dynamic((const void *)k_flush_wb<24>, nullptr));
         CKD(optin_dynamic((const void *)k_flush_wb<32>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_G<20>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_G<24>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_G<32>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_tma<20, 4, 3>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_tma<24, 4, 3>, nullptr));
+        CKD(optin_dynamic((const void *)k_flush_tma<32, 4, 3>, nullptr));
         // small lattices: the walker-resident kernel when at least two CTAs (walkers) share an SM
         {
             const size_t need = resident_smem_bytes(ns, n_up, n_dn, n_bonds);
@@ -1334,7 +1354,12 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;
     else if (n == "flush_variant") {
 #ifndef KDSL_DEV_VARIANTS
-        if (value != 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+        if (value == 3 && !h->Gbuf) {                    // the bulk-async path keeps G = -T Rt of every listed walker in global memory
+            int rc = use_device(h);
+            if (rc) return rc;
+            if ((rc = dev_alloc(h, &h->Gbuf, (size_t)2 * h->S.nw * h->Gstride))) return rc;
+        }
+        if (value != 0 && value != 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
 #endif
         h->flush_variant = (int)value;
     }
@@ -1371,6 +1396,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         h->gemm_variant = (int)value;
     }
     else if (n == "fused_ctas") h->fused_ctas = (int)value;
+    else if (n == "flush_dbg") h->flush_dbg = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
     return KDSL_OK;
