@@ -17,7 +17,7 @@
  *   - matrices are column-major (Julia layout): U is ns x N, W is ns x N with
  *     column l contiguous;
  *   - the bond list is Ham.nn in the reference's order
- *     (src/Hamiltonian.jl:370-373), pairs (i < j);
+ *     (src/Hamiltonian.jl:447-451), pairs (i < j);
  *   - one "sweep" is ONE proposed spin exchange per walker
  *     (src/MonteCarlo.jl:538-607).
  * W is real FP64 (valid for B = 0, where the mean-field Hamiltonian is real
@@ -75,7 +75,7 @@ int kdsl_device_count(int *n);
 /*
  * Create an engine on CUDA device `device`.
  * Replaces the state built by MC(params) / MC(Ham, kappa_up, kappa_down, W_up, W_down)
- * (src/MonteCarlo.jl:165-185, 209-234) from a Hamiltonian (src/Hamiltonian.jl:346-353):
+ * (src/MonteCarlo.jl:165-185, 209-234) from a Hamiltonian (src/Hamiltonian.jl:420-427):
  *   bonds  int32 [n_bonds][2]  Ham.nn, 1-based, reference order
  *   U_up   double [ns x n_up]  column-major Ham.U_up (real)
  *   U_dn   double [ns x n_dn]  column-major Ham.U_down

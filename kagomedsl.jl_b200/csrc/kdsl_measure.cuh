@@ -1,6 +1,6 @@
 // kdsl_measure.cuh -- Heisenberg local energy O_L per walker (reference getOL / getxprime /
-// spinInteraction! / SzInteraction! / Sz, src/Hamiltonian.jl:762-778, 597-605, 541-563, 501-512,
-// 445-476) and the full Z recount (src/MonteCarlo.jl:460-474).  One warp per walker, lanes
+// spinInteraction! / SzInteraction! / Sz, src/Hamiltonian.jl:762-778, 711-720, 636-672, 593-604,
+// 531-565) and the full Z recount (src/MonteCarlo.jl:460-474).  One warp per walker, lanes
 // stride over the bond list, warp-shuffle reduction.
 #pragma once
 #include "kdsl_common.cuh"
@@ -8,8 +8,8 @@
 #define KDSL_FLAG_BAD_SITE_DEV 4
 
 // OL = sum_bonds Sz_i Sz_j + sum_{antiparallel bonds} (-1/2) W_up[K_up, l_up] W_dn[K_dn, l_dn]
-//   j up & i down:  (K_up, l_up, K_dn, l_dn) = (i, kup[j], j, kdn[i])     :552-555
-//   i up & j down:  (j, kup[i], i, kdn[j])                               :557-560
+//   j up & i down:  (K_up, l_up, K_dn, l_dn) = (i, kup[j], j, kdn[i])     :649-657
+//   i up & j down:  (j, kup[i], i, kdn[j])                               :661-669
 // accumulate != 0: also feed the per-walker accumulators (Carlo.measure!, src/MonteCarlo.jl:628-634)
 __global__ void __launch_bounds__(256)
 k_measure(DevState S, double *__restrict__ ol_out, int accumulate) {
@@ -31,7 +31,7 @@ k_measure(DevState S, double *__restrict__ ol_out, int accumulate) {
             flips += -0.5 * Wu[(size_t)(ju - 1) * ns + i] * Wd[(size_t)(id - 1) * ns + j];
         if (iu != 0 && jd != 0)
             flips += -0.5 * Wu[(size_t)(iu - 1) * ns + j] * Wd[(size_t)(jd - 1) * ns + i];
-        // Sz(i) = +1/2 (up only), -1/2 (down only), else ArgumentError (:459-475)
+        // Sz(i) = +1/2 (up only), -1/2 (down only), else ArgumentError (:531-565)
         const int oi = (iu != 0) + (id != 0), oj = (ju != 0) + (jd != 0);
         if (oi != 1 || oj != 1) bad = 1;
         const int si = iu != 0 ? 1 : -1, sj = ju != 0 ? 1 : -1;

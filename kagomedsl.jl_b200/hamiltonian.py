@@ -16,12 +16,12 @@ import numpy as np
 
 from .lattice import AbstractLattice, DoubleKagome, ns as _ns
 
-# src/Hamiltonian.jl:176-191
+# src/Hamiltonian.jl:219-240
 pi_link_in: Dict[Tuple[int, int], int] = {
     (1, 2): 1, (1, 3): 1, (2, 3): 1, (2, 4): -1, (4, 6): 1, (4, 5): 1, (5, 6): 1,
     (2, 1): 1, (3, 1): 1, (3, 2): 1, (4, 2): -1, (6, 4): 1, (5, 4): 1, (6, 5): 1,
 }
-# src/Hamiltonian.jl:193-204
+# src/Hamiltonian.jl:250-261
 pi_link_inter: Dict[Tuple[int, int, int, int], int] = {
     (3, 5, -1, 1): -1, (3, 1, 0, 1): -1, (6, 2, 0, 1): -1, (6, 4, 0, 1): 1, (5, 1, 1, 0): 1,
     (1, 5, -1, 0): 1, (1, 3, 0, -1): -1, (2, 6, 0, -1): -1, (4, 6, 0, -1): 1, (5, 3, 1, -1): -1,
@@ -32,7 +32,7 @@ zero_link_inter = {k: 1 for k in pi_link_inter}
 
 
 def unitcell_coord(lat: AbstractLattice, s: int) -> np.ndarray:
-    """src/Hamiltonian.jl:17-27 (s is 1-based)"""
+    """src/Hamiltonian.jl:28-38 (s is 1-based)"""
     n1 = lat.n1 // 2
     n2 = lat.n2
     nsites = n1 * n2 * 6
@@ -42,7 +42,7 @@ def unitcell_coord(lat: AbstractLattice, s: int) -> np.ndarray:
 
 
 def unitcell_diff(lat: AbstractLattice, c1: Sequence[float], c2: Sequence[float]) -> Tuple[int, int]:
-    """src/Hamiltonian.jl:43-56"""
+    """src/Hamiltonian.jl:56-76"""
     d0, d1 = c1[0] - c2[0], c1[1] - c2[1]
     a1, a2 = lat.a1, lat.a2
     det = a1[0] * a2[1] - a1[1] * a2[0]
@@ -52,12 +52,12 @@ def unitcell_diff(lat: AbstractLattice, c1: Sequence[float], c2: Sequence[float]
 
 
 def get_site_coord(lat: AbstractLattice, s: int) -> np.ndarray:
-    """src/Hamiltonian.jl:220-224"""
+    """src/Hamiltonian.jl:279-283"""
     return unitcell_coord(lat, s) + lat.r[(s - 1) % 6]
 
 
 def get_boundary_shifts(lat: AbstractLattice, s1: int, s2: int) -> List[Tuple[int, int, float]]:
-    """src/Hamiltonian.jl:77-123: displacement of s2's cell from s1's plus its periodic images"""
+    """src/Hamiltonian.jl:99-153: displacement of s2's cell from s1's plus its periodic images"""
     assert s1 != s2, f"s1 and s2 should not be the same, got: {s1} and {s2}"
     PBC1, PBC2 = lat.PBC
     anti1, anti2 = lat.antiPBC
@@ -86,7 +86,7 @@ def get_boundary_shifts(lat: AbstractLattice, s1: int, s2: int) -> List[Tuple[in
 
 def apply_boundary_conditions_(tunneling: np.ndarray, lat: AbstractLattice, s1: int, s2: int,
                                link_inter: Dict, B: float) -> None:
-    """`apply_boundary_conditions!` (src/Hamiltonian.jl:145-174); tunneling is modified in place"""
+    """`apply_boundary_conditions!` (src/Hamiltonian.jl:177-207); tunneling is modified in place"""
     nsites = (lat.n1 // 2) * lat.n2 * 6
     assert 1 <= s1 <= nsites and 1 <= s2 <= nsites, "site index out of range"
     cell1, cell2 = (s1 - 1) // 6 + 1, (s2 - 1) // 6 + 1
@@ -104,7 +104,7 @@ def apply_boundary_conditions_(tunneling: np.ndarray, lat: AbstractLattice, s1: 
 
 
 def Hmat(lat: DoubleKagome, link_in: Dict = None, link_inter: Dict = None, B: float = 0.0) -> np.ndarray:
-    """`Hmat(lat; link_in, link_inter, B)` (src/Hamiltonian.jl:247-289): ns x ns complex Hermitian
+    """`Hmat(lat; link_in, link_inter, B)` (src/Hamiltonian.jl:308-354): ns x ns complex Hermitian
     hopping matrix, H = -(T + T') with T strictly upper triangular."""
     link_in = pi_link_in if link_in is None else link_in
     link_inter = pi_link_inter if link_inter is None else link_inter
@@ -166,7 +166,7 @@ def Hmat(lat: DoubleKagome, link_in: Dict = None, link_inter: Dict = None, B: fl
 
 
 def orbitals(H_mat: np.ndarray, N_up: int, N_down: int):
-    """src/Hamiltonian.jl:314-322: lowest-N eigenvectors of Hermitian(H_mat) as columns.
+    """src/Hamiltonian.jl:382-393: lowest-N eigenvectors of Hermitian(H_mat) as columns.
     A real H (B = 0) is diagonalised as real symmetric so that U, hence W, is real FP64."""
     if np.iscomplexobj(H_mat) and np.abs(H_mat.imag).max(initial=0.0) == 0.0:
         w, v = np.linalg.eigh(np.ascontiguousarray(H_mat.real))
@@ -178,14 +178,14 @@ def orbitals(H_mat: np.ndarray, N_up: int, N_down: int):
 
 
 def get_nn(H_mat: np.ndarray) -> List[Tuple[int, int]]:
-    """src/Hamiltonian.jl:370-373: `findall(!iszero, UpperTriangular(H))` -- 1-based (i, j) pairs in
+    """src/Hamiltonian.jl:447-451: `findall(!iszero, UpperTriangular(H))` -- 1-based (i, j) pairs in
     column-major order"""
     jj, ii = np.nonzero(np.triu(np.asarray(H_mat)).T)
     return [(int(i) + 1, int(j) + 1) for i, j in zip(ii, jj)]
 
 
 class Hamiltonian:
-    """`struct Hamiltonian` (src/Hamiltonian.jl:346-353) with both reference constructors:
+    """`struct Hamiltonian` (src/Hamiltonian.jl:420-427) with both reference constructors:
     Hamiltonian(N_up, N_down, lat; link_in, link_inter, B)            (:399-411)
     Hamiltonian(N_up, N_down, U_up, U_down, H_mat, nn)                (field constructor)"""
 
@@ -219,7 +219,7 @@ def is_occupied(kappa: Sequence[int], l: int) -> bool:
 
 
 def Sz(i: int, kappa_up: Sequence[int], kappa_down: Sequence[int]) -> float:
-    """src/Hamiltonian.jl:445-476"""
+    """src/Hamiltonian.jl:531-565"""
     n = len(kappa_up)
     if not 1 <= i <= n:
         raise IndexError(f"BoundsError: attempt to access {n}-element vector at index [{i}]")
@@ -236,13 +236,13 @@ def Sz(i: int, kappa_up: Sequence[int], kappa_down: Sequence[int]) -> float:
 
 
 def SzInteraction_(xprime: Dict, kappa_up, kappa_down, i: int, j: int) -> None:
-    """`SzInteraction!` (src/Hamiltonian.jl:501-512)"""
+    """`SzInteraction!` (src/Hamiltonian.jl:593-604)"""
     key = (-1, -1, -1, -1)
     xprime[key] = xprime.get(key, 0.0) + Sz(i, kappa_up, kappa_down) * Sz(j, kappa_up, kappa_down)
 
 
 def spinInteraction_(xprime: Dict, kappa_up, kappa_down, i: int, j: int) -> None:
-    """`spinInteraction!` (src/Hamiltonian.jl:541-563): keys (K_up, l_up, K_down, l_down) += -1/2"""
+    """`spinInteraction!` (src/Hamiltonian.jl:636-672): keys (K_up, l_up, K_down, l_down) += -1/2"""
     i_up, j_up = kappa_up[i - 1], kappa_up[j - 1]
     i_down, j_down = kappa_down[i - 1], kappa_down[j - 1]
     if j_up != 0 and i_down != 0:
@@ -254,7 +254,7 @@ def spinInteraction_(xprime: Dict, kappa_up, kappa_down, i: int, j: int) -> None
 
 
 def getxprime(Ham: Hamiltonian, kappa_up, kappa_down) -> Dict[Tuple[int, int, int, int], float]:
-    """src/Hamiltonian.jl:597-605 (host utility; on the GPU this expansion is fused into k_measure)"""
+    """src/Hamiltonian.jl:711-720 (host utility; on the GPU this expansion is fused into k_measure)"""
     xprime: Dict[Tuple[int, int, int, int], float] = {}
     for (i, j) in Ham.nn:
         spinInteraction_(xprime, kappa_up, kappa_down, i, j)

@@ -16,7 +16,7 @@
  *
  * Two scalar instantiations of the MC core are generated from
  * oracle_mc_core.inc: c128 (ComplexF64, the reference's storage type,
- * src/Hamiltonian.jl:346-353) and f64 (real, valid for B = 0).
+ * src/Hamiltonian.jl:420-427) and f64 (real, valid for B = 0).
  */
 #include <complex.h>
 #include <math.h>
@@ -58,7 +58,7 @@ int ko_lattice_init(ko_lattice *lat, double t, int n1, int n2, int pbc1, int pbc
 /* src/Lattice.jl:97 */
 int ko_ns(const ko_lattice *lat) { return lat->n1 * lat->n2 * 3; }
 
-/* src/Hamiltonian.jl:17-27 unitcell_coord (s is 1-based). returns -1 on the @assert */
+/* src/Hamiltonian.jl:28-38 unitcell_coord (s is 1-based). returns -1 on the @assert */
 int ko_unitcell_coord(const ko_lattice *lat, int s, double out[2]) {
     int n1 = lat->n1 / 2, n2 = lat->n2;
     int ns = n1 * n2 * 6;
@@ -69,7 +69,7 @@ int ko_unitcell_coord(const ko_lattice *lat, int s, double out[2]) {
     return 0;
 }
 
-/* src/Hamiltonian.jl:43-56 unitcell_diff */
+/* src/Hamiltonian.jl:56-76 unitcell_diff */
 void ko_unitcell_diff(const ko_lattice *lat, const double c1[2], const double c2[2],
                       int *dx, int *dy) {
     double d0 = c1[0] - c2[0], d1 = c1[1] - c2[1];
@@ -79,7 +79,7 @@ void ko_unitcell_diff(const ko_lattice *lat, const double c1[2], const double c2
     *dy = (int)rint((-a1[1] * d0 + a1[0] * d1) / det);
 }
 
-/* src/Hamiltonian.jl:220-224 get_site_coord */
+/* src/Hamiltonian.jl:279-283 get_site_coord */
 int ko_get_site_coord(const ko_lattice *lat, int s, double out[2]) {
     int label = (s - 1) % 6;
     double uc[2];
@@ -89,7 +89,7 @@ int ko_get_site_coord(const ko_lattice *lat, int s, double out[2]) {
     return 0;
 }
 
-/* src/Hamiltonian.jl:77-123 get_boundary_shifts.
+/* src/Hamiltonian.jl:99-153 get_boundary_shifts.
  * out: up to 9 triples (dx, dy, sign). returns count, or -1 on an @assert. */
 int ko_get_boundary_shifts(const ko_lattice *lat, int s1, int s2, int out_dx[9],
                            int out_dy[9], double out_sign[9]) {
@@ -126,8 +126,8 @@ int ko_get_boundary_shifts(const ko_lattice *lat, int s1, int s2, int out_dx[9],
 }
 
 /* link tables are passed as flat int arrays:
- *   link_in   [n_in][3]    = (label1, label2, value)          src/Hamiltonian.jl:176-191
- *   link_inter[n_inter][5] = (label1, label2, dx, dy, value)  src/Hamiltonian.jl:193-204 */
+ *   link_in   [n_in][3]    = (label1, label2, value)          src/Hamiltonian.jl:219-240
+ *   link_inter[n_inter][5] = (label1, label2, dx, dy, value)  src/Hamiltonian.jl:250-261 */
 static int find_link_in(const int *t, int n, int l1, int l2, int *val) {
     for (int q = 0; q < n; q++)
         if (t[3 * q] == l1 && t[3 * q + 1] == l2) { *val = t[3 * q + 2]; return 1; }
@@ -142,7 +142,7 @@ static int find_link_inter(const int *t, int n, int l1, int l2, int dx, int dy, 
     return 0;
 }
 
-/* src/Hamiltonian.jl:145-174 apply_boundary_conditions!  (tunneling col-major ns x ns)
+/* src/Hamiltonian.jl:177-207 apply_boundary_conditions!  (tunneling col-major ns x ns)
  * returns 0, or -1 on an @assert (same cell / bad index) */
 int ko_apply_boundary_conditions(double _Complex *tunneling, int ld, const ko_lattice *lat,
                                  int s1, int s2, const int *link_inter, int n_inter,
@@ -177,7 +177,7 @@ int ko_apply_boundary_conditions(double _Complex *tunneling, int ld, const ko_la
     return 0;
 }
 
-/* src/Hamiltonian.jl:247-289 Hmat.  H col-major ns x ns (complex).
+/* src/Hamiltonian.jl:308-354 Hmat.  H col-major ns x ns (complex).
  * returns 0 ok, -3 "tunneling matrix must be upper triangular" */
 int ko_hmat(const ko_lattice *lat, const int *link_in, int n_in, const int *link_inter,
             int n_inter, double B, double _Complex *H) {
@@ -217,7 +217,7 @@ int ko_hmat(const ko_lattice *lat, const int *link_in, int n_in, const int *link
     return 0;
 }
 
-/* src/Hamiltonian.jl:370-373 get_nn: findall(!iszero, UpperTriangular(H)) in
+/* src/Hamiltonian.jl:447-451 get_nn: findall(!iszero, UpperTriangular(H)) in
  * column-major order -> (i, j) 1-based pairs with i <= j.  returns n_bonds. */
 int ko_get_nn(const double _Complex *H, int ns, int32_t *bonds, int max_bonds) {
     int n = 0;
@@ -285,7 +285,7 @@ int ko_Z(const int32_t *bonds, int n_bonds, const int64_t *kup, const int64_t *k
     return count;
 }
 
-/* src/Hamiltonian.jl:445-476 Sz.  returns 0 and *out = +-0.5, or -1 (doubly occupied),
+/* src/Hamiltonian.jl:531-565 Sz.  returns 0 and *out = +-0.5, or -1 (doubly occupied),
  * -2 (unoccupied) [ArgumentError], -3 BoundsError */
 int ko_Sz(int i, const int64_t *kup, const int64_t *kdn, int n, double *out) {
     if (!(1 <= i && i <= n)) return -3;
@@ -296,7 +296,7 @@ int ko_Sz(int i, const int64_t *kup, const int64_t *kdn, int n, double *out) {
     return -2;
 }
 
-/* src/Hamiltonian.jl:541-563 spinInteraction! + :501-512 SzInteraction! + :597-605 getxprime,
+/* src/Hamiltonian.jl:636-672 spinInteraction! + :593-604 SzInteraction! + :711-720 getxprime,
  * flattened: for each bond emits up to two flip keys (K_up, l_up, K_down, l_down) with
  * coefficient -1/2, and accumulates the diagonal Sz_i*Sz_j sum.  keys: [max_keys][4] 1-based.
  * Distinct bonds always give distinct keys (the key contains both sites), so this flat list is
@@ -308,14 +308,14 @@ int ko_getxprime(const int32_t *bonds, int n_bonds, const int64_t *kup, const in
     for (int b = 0; b < n_bonds; b++) {
         int i = bonds[2 * b], j = bonds[2 * b + 1];
         int64_t i_up = kup[i - 1], j_up = kup[j - 1], i_dn = kdn[i - 1], j_dn = kdn[j - 1];
-        if (j_up != 0 && i_dn != 0) {                     /* :552-555 */
+        if (j_up != 0 && i_dn != 0) {                     /* :649-657 */
             if (nk < max_keys) {
                 keys[4 * nk] = i; keys[4 * nk + 1] = j_up; keys[4 * nk + 2] = j; keys[4 * nk + 3] = i_dn;
                 coefs[nk] = -1.0 / 2.0;
             }
             nk++;
         }
-        if (i_up != 0 && j_dn != 0) {                     /* :557-560 */
+        if (i_up != 0 && j_dn != 0) {                     /* :661-669 */
             if (nk < max_keys) {
                 keys[4 * nk] = j; keys[4 * nk + 1] = i_up; keys[4 * nk + 2] = i; keys[4 * nk + 3] = j_dn;
                 coefs[nk] = -1.0 / 2.0;

@@ -66,7 +66,7 @@ def _p(a):
 
 
 # ----------------------------------------------------------------------------
-# link tables (src/Hamiltonian.jl:176-204 and scripts/zero_flux.jl:15-42)
+# link tables (src/Hamiltonian.jl:219-261 and scripts/zero_flux.jl:15-42)
 # ----------------------------------------------------------------------------
 PI_LINK_IN = {(1, 2): 1, (1, 3): 1, (2, 3): 1, (2, 4): -1, (4, 6): 1, (4, 5): 1, (5, 6): 1,
               (2, 1): 1, (3, 1): 1, (3, 2): 1, (4, 2): -1, (6, 4): 1, (5, 4): 1, (6, 5): 1}
@@ -140,7 +140,7 @@ class Lattice:
             raise AssertionError("apply_boundary_conditions! assertion")
 
     def hmat(self, link_in=None, link_inter=None, B=0.0):
-        """Hmat(lat; link_in, link_inter, B)  -- src/Hamiltonian.jl:247-289"""
+        """Hmat(lat; link_in, link_inter, B)  -- src/Hamiltonian.jl:308-354"""
         li = _flat_in(PI_LINK_IN if link_in is None else link_in)
         lx = _flat_inter(PI_LINK_INTER if link_inter is None else link_inter)
         ns = self.ns
@@ -152,7 +152,7 @@ class Lattice:
 
 
 def get_nn(H):
-    """get_nn(H_mat) -- src/Hamiltonian.jl:370-373; returns int32 [n_bonds, 2] 1-based pairs"""
+    """get_nn(H_mat) -- src/Hamiltonian.jl:447-451; returns int32 [n_bonds, 2] 1-based pairs"""
     H = np.asfortranarray(H, dtype=np.complex128)
     ns = H.shape[0]
     n = lib().ko_get_nn(_p(H), ns, None, 0)
@@ -162,7 +162,7 @@ def get_nn(H):
 
 
 def orbitals(H, N_up, N_down):
-    """orbitals(H_mat, N_up, N_down) -- src/Hamiltonian.jl:314-322 (eigen(Hermitian) -> lowest-N
+    """orbitals(H_mat, N_up, N_down) -- src/Hamiltonian.jl:382-393 (eigen(Hermitian) -> lowest-N
     eigenvectors).  LAPACK via numpy; the eigenvector gauge is unpinned (W is gauge invariant for
     closed shells).  Real H (B = 0) is diagonalised as a real symmetric matrix so U is real."""
     if np.abs(H.imag).max() == 0.0:
