@@ -177,6 +177,22 @@ int kdsl_accumulators(kdsl_handle h, double *out, int64_t *acc_per_walker,
                       double *ol_sum_per_walker);
 int kdsl_reset_accumulators(kdsl_handle h);
 
+/*
+ * Extra observables taken with every :OL sample (not in the reference; the hook is register_evaluables,
+ * src/MonteCarlo.jl:675-687).  After kdsl_set_observables(h, nq, cos_qr, sin_qr) with
+ * cos_qr / sin_qr = double [nq][ns] holding cos(q . r_i) / sin(q . r_i) for the wave vectors of interest (nq may be 0),
+ * every cadence measurement also accumulates, per walker,
+ *   S(q) = |sum_i exp(i q r_i) Sz_i|^2 / ns      the longitudinal spin structure factor (from kappa alone), and
+ *   Z_mu, OL * Z_mu, S(q) * Z_mu                 the weights that turn chain averages into |psi|^2 averages: the
+ *                                                chain of src/MonteCarlo.jl:538-607 samples |psi|^2 / Z_mu, so
+ *                                                <O>_psi = <O Z_mu> / <Z_mu>.
+ * kdsl_get_observables returns the sums over this handle's walkers (over all ranks if allreduce != 0 and a communicator
+ * exists): out[0] = samples, [1] = sum Z_mu, [2] = sum OL Z_mu, [3] = 0, [4 .. 4+nq) = sum S(q), [4+nq .. 4+2nq) =
+ * sum S(q) Z_mu.  kdsl_reset_accumulators clears them.
+ */
+int kdsl_set_observables(kdsl_handle h, int nq, const double *cos_qr, const double *sin_qr);
+int kdsl_get_observables(kdsl_handle h, double *out, int allreduce);
+
 /* Copy one walker's W matrix to the host: spin 0 = up (ns x n_up), 1 = down (ns x n_dn) */
 int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out);
 /* Overwrite one walker's W matrix (test hook for the update_W! known answers) */

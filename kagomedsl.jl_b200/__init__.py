@@ -9,7 +9,7 @@ from .hamiltonian import (Hamiltonian, Hmat, Sz, SzInteraction_, apply_boundary_
                           spinInteraction_, unitcell_coord, unitcell_diff, zero_link_in, zero_link_inter)
 from .montecarlo import (MC, AbstractMC, Engine, Evaluator, MCContext, Z, accumulators, find_initial_configuration_,
                          getOL, init_, init_conf_qr, measure_, read_checkpoint_, reevaluateW_, register_evaluables,
-                         run_, step_, sweep_, tilde_U, write_checkpoint)
+                         run_, step_, sweep_, tilde_U, write_checkpoint, save_checkpoint_npz, load_checkpoint_npz)
 from ._lib import KdslError, SingularException
 from .rng import Xoshiro, walker_states
 from . import dist

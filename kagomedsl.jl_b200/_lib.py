@@ -33,7 +33,7 @@ SYMBOLS = (
     "kdsl_accumulators", "kdsl_reset_accumulators", "kdsl_get_W", "kdsl_set_W", "kdsl_update_W",
     "kdsl_get_Z", "kdsl_get_flags", "kdsl_set_profiling", "kdsl_timers", "kdsl_reset_timers",
     "kdsl_set_option", "kdsl_synchronize", "kdsl_info", "kdsl_event_record", "kdsl_event_elapsed", "kdsl_bench_fp64_dmma",
-    "kdsl_bench_fp64_dmma_sustained",
+    "kdsl_bench_fp64_dmma_sustained", "kdsl_set_observables", "kdsl_get_observables",
     "kdsl_comm_version", "kdsl_comm_unique_id", "kdsl_comm_init_rank", "kdsl_comm_init_all", "kdsl_comm_info",
     "kdsl_comm_destroy", "kdsl_accumulators_allreduce", "kdsl_group_accumulators_allreduce",
 )
@@ -107,6 +107,8 @@ def lib():
         L.kdsl_bench_fp64_dmma.argtypes = [vp, C.POINTER(C.c_double)]
         L.kdsl_bench_fp64_dmma_sustained.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.kdsl_event_elapsed.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
+        L.kdsl_set_observables.argtypes = [vp, i32, vp, vp]
+        L.kdsl_get_observables.argtypes = [vp, vp, i32]
         L.kdsl_comm_version.argtypes = [C.POINTER(i32)]
         L.kdsl_comm_unique_id.argtypes = [vp]
         L.kdsl_comm_init_rank.argtypes = [vp, i32, i32, vp]

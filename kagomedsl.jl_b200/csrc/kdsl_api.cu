@@ -91,6 +91,7 @@ struct kdsl_handle_s {
     int *d_tmp_i = nullptr;       // [nw] scratch
     double *d_tmp_d = nullptr;    // [nw] scratch
     double *d_acc8 = nullptr;     // [8]
+    double *d_qcos = nullptr, *d_qsin = nullptr, *d_obs = nullptr;   // extra observables (kdsl_set_observables)
     // replay staging (device)
     double *rp_r = nullptr;
     int *rp_bond = nullptr, *rp_pick = nullptr;
@@ -646,6 +647,10 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
             else if (h->cplx) k_measure_c<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             else k_measure<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
             CK(cudaGetLastError());
+            if (S.obs_on) {
+                k_measure_extra<<<pgrid, 256, 0, h->stream>>>(S);
+                CK(cudaGetLastError());
+            }
         }
         if (h->profiling && h->spans.size() > 16384) {
             int rc = flush_spans(h);
@@ -963,6 +968,10 @@ int kdsl_destroy(kdsl_handle h) {
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->user_ev) if (e) cudaEventDestroy(e);
     for (void *p : h->allocs) cudaFree(p);
+    if (h->d_qcos) cudaFree(h->d_qcos);
+    if (h->d_qsin) cudaFree(h->d_qsin);
+    if (h->d_obs) cudaFree(h->d_obs);
+    if (h->S.obs_w) cudaFree(h->S.obs_w);
     if (h->rp_r) { cudaFree(h->rp_r); cudaFree(h->rp_bond); cudaFree(h->rp_pick); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1179,9 +1188,37 @@ int kdsl_reset_accumulators(kdsl_handle h) {
     CK(cudaMemsetAsync(S.ol_sq, 0, nw * 8, h->stream));
     CK(cudaMemsetAsync(S.ol_n, 0, nw * 8, h->stream));
     CK(cudaMemsetAsync(S.cnt + 3, 0, sizeof(int), h->stream));
+    if (S.obs_w) CK(cudaMemsetAsync(S.obs_w, 0, nw * (4 + 2 * (size_t)S.nq) * sizeof(double), h->stream));
     h->walker_sweeps = 0;
     return KDSL_OK;
 }
+
+int kdsl_set_observables(kdsl_handle h, int nq, const double *cos_qr, const double *sin_qr) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (nq < 0 || nq > 4096 || (nq > 0 && (!cos_qr || !sin_qr)))
+        return fail(KDSL_ERR_INVALID_ARGUMENT, "need 0 <= nq <= 4096 and both phase tables");
+    DevState &S = h->S;
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t nw = S.nw, ns = S.ns;
+    auto renew = [&](double **p, size_t n) -> cudaError_t {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(double));
+    };
+    CK(renew(&h->d_qcos, (size_t)nq * ns));
+    CK(renew(&h->d_qsin, (size_t)nq * ns));
+    CK(renew(&h->d_obs, 4 + 2 * (size_t)nq));
+    CK(renew(&S.obs_w, nw * (4 + 2 * (size_t)nq)));
+    if (nq > 0) {
+        CK(cudaMemcpy(h->d_qcos, cos_qr, (size_t)nq * ns * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_qsin, sin_qr, (size_t)nq * ns * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemset(S.obs_w, 0, nw * (4 + 2 * (size_t)nq) * sizeof(double)));
+    S.q_cos = h->d_qcos; S.q_sin = h->d_qsin; S.nq = nq; S.obs_on = 1;
+    return KDSL_OK;
+}
+
 
 int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     int rc = use_device(h);
@@ -1629,6 +1666,21 @@ int kdsl_group_accumulators_allreduce(int n, kdsl_handle *handles, double *out) 
         CK(cudaSetDevice(handles[i]->device));
         CK(cudaStreamSynchronize(handles[i]->stream));
     }
+    return KDSL_OK;
+}
+
+int kdsl_get_observables(kdsl_handle h, double *out, int allreduce) {
+    int rc = use_device(h);
+    if (rc) return rc;
+    const DevState &S = h->S;
+    if (!S.obs_on) return fail(KDSL_ERR_STATE, "no extra observables: call kdsl_set_observables first");
+    if (!out) return fail(KDSL_ERR_INVALID_ARGUMENT, "out is null");
+    const int n = 4 + 2 * S.nq;
+    k_reduce_obs<<<(n + 127) / 128, 128, 0, h->stream>>>(S, h->d_obs);
+    CK(cudaGetLastError());
+    if (allreduce && h->comm) NCK(g_nccl.AllReduce(h->d_obs, h->d_obs, n, ncclDouble, ncclSum, h->comm, h->stream));
+    CK(cudaMemcpyAsync(out, h->d_obs, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return KDSL_OK;
 }
 

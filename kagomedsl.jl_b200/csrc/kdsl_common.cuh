@@ -44,6 +44,11 @@ struct DevState {
     int *flush_list;             // [nw] walkers that reached kth pending factors (count in cnt[4])
     int *listed;                 // [nw] 1 while the walker sits in flush_list (a walker is listed at most once)
     int kmax, kth;
+    // optional extra observables taken with every :OL sample (kdsl_set_observables):
+    // obs_w [nw][4 + 2 nq] = n, sum Z_mu, sum OL Z_mu, -, sum S(q) [nq], sum S(q) Z_mu [nq]
+    int obs_on, nq;
+    const double *q_cos, *q_sin;     // [nq][ns] cos(q . r_i), sin(q . r_i)
+    double *obs_w;
 };
 
 __device__ __forceinline__ unsigned long long rotl64(unsigned long long x, int k) {

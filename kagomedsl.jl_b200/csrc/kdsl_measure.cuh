@@ -53,6 +53,57 @@ k_measure(DevState S, double *__restrict__ ol_out, int accumulate) {
     }
 }
 
+// Extra observables of one walker (whole warp), taken together with an :OL sample:
+//   S(q) = |sum_i exp(i q r_i) Sz_i|^2 / ns   (longitudinal spin structure factor, from kappa alone), and the weights that
+//   turn chain averages into |psi|^2 averages: the chain's stationary law is |psi|^2 / Z_mu, so
+//   <O>_psi = <O Z_mu> / <Z_mu>.  `up(i)` tells whether site i carries an up spin.
+template <typename UpFn>
+__device__ __forceinline__ void extra_observables_warp(const DevState &S, int w, int lane, int zmu, double OL, UpFn up) {
+    double *obs = S.obs_w + (size_t)w * (4 + 2 * S.nq);
+    const double z = (double)zmu;
+    for (int q = 0; q < S.nq; q++) {
+        const double *c = S.q_cos + (size_t)q * S.ns, *s = S.q_sin + (size_t)q * S.ns;
+        double re = 0.0, im = 0.0;
+        for (int i = lane; i < S.ns; i += 32) {
+            const double sz = up(i) ? 0.5 : -0.5;
+            re = fma(__ldg(c + i), sz, re);
+            im = fma(__ldg(s + i), sz, im);
+        }
+        re = warp_sum_f64(re);
+        im = warp_sum_f64(im);
+        if (lane == 0) {
+            const double sq = (re * re + im * im) / (double)S.ns;
+            obs[4 + q] += sq;
+            obs[4 + S.nq + q] += sq * z;
+        }
+    }
+    if (lane == 0) {
+        obs[0] += 1.0;
+        obs[1] += z;
+        obs[2] += OL * z;
+    }
+}
+
+// ... for every walker, right after the cadence measurement wrote ol_last (the lock-step paths); one warp per walker
+__global__ void __launch_bounds__(256) k_measure_extra(DevState S) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= S.nw) return;
+    if (S.flags[w] & 1) return;                                 // frozen after a singular re-evaluation: no sample
+    const int *kup = S.kup + (size_t)w * S.ns;
+    extra_observables_warp(S, w, lane, S.zmu[w], S.ol_last[w], [&](int i) { return kup[i] != 0; });
+}
+
+// sums of obs_w over the walkers: one thread per observable index
+__global__ void k_reduce_obs(DevState S, double *__restrict__ out) {
+    const int n = 4 + 2 * S.nq;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    double a = 0.0;
+    for (int w = 0; w < S.nw; w++) a += S.obs_w[(size_t)w * n + x];
+    out[x] = a;
+}
+
 // Z(nn, kappa_up, kappa_down): full recount.  store != 0 writes it to S.zmu (after set_config),
 // otherwise to out (verification of the incremental value).
 __global__ void __launch_bounds__(256) k_count_Z(DevState S, int *__restrict__ out, int store) {

@@ -24,6 +24,7 @@
 #pragma once
 #include "kdsl_common.cuh"
 #include "kdsl_propose.cuh"
+#include "kdsl_measure.cuh"
 #include "kdsl_refresh.cuh"
 #include <type_traits>
 
@@ -604,6 +605,11 @@ k_resident(DevState S, ResParams P) {
                 if (tid == 0) {
                     if (bad) atomicOr(&S.flags[w], 4);
                     a_ol += OL; a_ol2 += OL * OL; c_ol += 1ull; last_ol = OL; have_ol = true;
+                }
+                if (S.obs_on && warp == 0) {                     // structure factor / reweighting sums (kdsl_set_observables)
+                    const double OLb = __shfl_sync(0xffffffffu, OL, 0);
+                    const short *ku = L.kap(0);
+                    extra_observables_warp(S, w, lane, zmu, OLb, [&](int i) { return ku[i] != 0; });
                 }
             }
             if (ev & RES_EV_DONE) break;

@@ -37,8 +37,7 @@ mutable struct MC <: AbstractMC
     ns::Int
     n_walkers::Int
     sweeps_per_call::Int
-    acc_seen::Float64
-    ws_seen::Float64
+    acc_seen::Vector{Int64}          # per-walker accepted-move counts already reported as :acc
 end
 
 function MC(params::AbstractDict)
@@ -61,7 +60,7 @@ function MC(params::AbstractDict)
                     (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint, Ptr{Int32}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint),
                     h, dev, ns, Ham.N_up, Ham.N_down, length(Ham.nn), bonds, Uu, Ud, nw))
     end
-    mc = MC(Ham, h[], ns, nw, get(params, :sweeps_per_call, 1), 0.0, 0.0)
+    mc = MC(Ham, h[], ns, nw, get(params, :sweeps_per_call, 1), zeros(Int64, nw))
     finalizer(m -> ccall((:kdsl_destroy, libkdsl), Cint, (Ptr{Cvoid},), m.handle), mc)
     return mc
 end
@@ -87,14 +86,17 @@ function Carlo.init!(mc::MC, ctx::MCContext, params::AbstractDict)
         rethrow(e)
     end
     check(ccall((:kdsl_reset_accumulators, libkdsl), Cint, (Ptr{Cvoid},), mc.handle))
+    fill!(mc.acc_seen, 0)
     return nothing
 end
 
+"sums over this handle's walkers (KDSL_ACC_* order) and the per-walker accepted-move counts"
 function accumulators(mc::MC)
     out = zeros(Float64, 8)
+    acc_w = zeros(Int64, mc.n_walkers)
     check(ccall((:kdsl_accumulators, libkdsl), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
-                mc.handle, out, C_NULL, C_NULL))
-    return out
+                mc.handle, out, acc_w, C_NULL))
+    return out, acc_w
 end
 
 # Carlo.sweep! (src/MonteCarlo.jl:538-607) for every walker
@@ -102,11 +104,13 @@ function Carlo.sweep!(mc::MC, ctx::MCContext)
     k = mc.sweeps_per_call
     check(ccall((:kdsl_set_sweeps, libkdsl), Cint, (Ptr{Cvoid}, Int64), mc.handle, ctx.sweeps * k))
     check(ccall((:kdsl_sweep, libkdsl), Cint, (Ptr{Cvoid}, Int64, Int64), mc.handle, k, -1))
-    a = accumulators(mc)
+    a, acc_w = accumulators(mc)
     a[8] > 0 && throw(LinearAlgebra.SingularException(0))           # KDSL_ACC_N_SINGULAR
-    dacc = a[2] - mc.acc_seen; dws = a[1] - mc.ws_seen
-    mc.acc_seen = a[2]; mc.ws_seen = a[1]
-    measure!(ctx, :acc, dws > 0 ? dacc / dws : 0.0)
+    # :acc (src/MonteCarlo.jl:548-589): the reference records 0.0 / 1.0 for its one walker; a batch records the vector of
+    # the walkers' acceptance fractions over this call (a Carlo vector observable: one chain per component)
+    d = (acc_w .- mc.acc_seen) ./ k
+    mc.acc_seen .= acc_w
+    measure!(ctx, :acc, mc.n_walkers == 1 ? d[1] : d)
     return nothing
 end
 
@@ -153,6 +157,47 @@ function Carlo.read_checkpoint!(mc::MC, in::HDF5.Group)
     end
     load_configuration!(mc, ku, kd)
     return nothing
+end
+
+# ---- multi-GPU in one Julia process: one MC (handle) per device, NCCL sum of the accumulators inside libkdsl ----
+"ncclCommInitAll over the handles' devices (kdsl_comm_init_all)"
+function comm_init_all(mcs::Vector{MC})
+    hs = Ptr{Cvoid}[m.handle for m in mcs]
+    check(ccall((:kdsl_comm_init_all, libkdsl), Cint, (Cint, Ptr{Ptr{Cvoid}}), length(hs), hs))
+end
+
+"global sums (KDSL_ACC_* order) over all handles: one grouped ncclAllReduce of 8 doubles"
+function accumulators_allreduce(mcs::Vector{MC})
+    hs = Ptr{Cvoid}[m.handle for m in mcs]
+    out = zeros(Float64, 8)
+    check(ccall((:kdsl_group_accumulators_allreduce, libkdsl), Cint, (Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}), length(hs), hs, out))
+    return out
+end
+
+# one process per GPU (Carlo's MPI ranks): rank 0 calls comm_unique_id(), ships the 128 bytes (MPI.Bcast!), all call comm_init_rank!
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:kdsl_comm_unique_id, libkdsl), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init_rank!(mc::MC, n_ranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:kdsl_comm_init_rank, libkdsl), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), mc.handle, n_ranks, rank, id))
+function accumulators_allreduce(mc::MC)
+    out = zeros(Float64, 8)
+    check(ccall((:kdsl_accumulators_allreduce, libkdsl), Cint, (Ptr{Cvoid}, Ptr{Float64}), mc.handle, out))
+    return out
+end
+
+# ---- extra observables (structure factor at the wave vectors qs [2 x nq], Z_mu-reweighted |psi|^2 averages) ----
+function set_observables!(mc::MC, qs::AbstractMatrix{<:Real}, coords::AbstractMatrix{<:Real})   # coords: 2 x ns
+    ph = transpose(coords) * qs                                     # ns x nq, column q contiguous = [nq][ns] in C
+    c = Matrix{Float64}(cos.(ph)); s = Matrix{Float64}(sin.(ph))
+    check(ccall((:kdsl_set_observables, libkdsl), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), mc.handle, size(qs, 2), c, s))
+end
+function observables(mc::MC, nq::Integer; allreduce::Bool = false)
+    out = zeros(Float64, 4 + 2nq)
+    check(ccall((:kdsl_get_observables, libkdsl), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), mc.handle, out, allreduce))
+    return out
 end
 
 export MC

@@ -240,6 +240,32 @@ class Engine:
     def reset_accumulators(self):
         check(self._L.kdsl_reset_accumulators(self._h))
 
+    # -- extra observables ------------------------------------------------
+    def set_observables(self, q_vectors=None, coords=None) -> None:
+        """enable the structure factor S(q) at the given wave vectors ([nq, 2]; `coords` = site positions [ns, 2]) and the
+        Z_mu reweighting sums; with no wave vectors only the reweighting sums are taken"""
+        if q_vectors is None or len(q_vectors) == 0:
+            self._nq = 0
+            check(self._L.kdsl_set_observables(self._h, 0, None, None))
+            return
+        q = np.asarray(q_vectors, dtype=np.float64).reshape(-1, 2)
+        r = np.asarray(coords, dtype=np.float64).reshape(self.ns, 2)
+        ph = q @ r.T                                                    # [nq, ns]
+        c, s = np.ascontiguousarray(np.cos(ph)), np.ascontiguousarray(np.sin(ph))
+        self._nq = q.shape[0]
+        check(self._L.kdsl_set_observables(self._h, self._nq, _ptr(c), _ptr(s)))
+
+    def observables(self, allreduce: bool = False) -> Dict[str, np.ndarray]:
+        """sums and the derived estimators: chain averages (law |psi|^2 / Z_mu) and |psi|^2 averages (reweighted)"""
+        nq = getattr(self, "_nq", 0)
+        out = np.zeros(4 + 2 * nq)
+        check(self._L.kdsl_get_observables(self._h, _ptr(out), int(bool(allreduce))))
+        n, z, olz = out[0], out[1], out[2]
+        sq, sqz = out[4:4 + nq], out[4 + nq:]
+        return {"n": n, "sum_Z": z, "sum_OL_Z": olz, "sum_Sq": sq, "sum_Sq_Z": sqz,
+                "energy_psi2": olz / z / self.ns if z else float("nan"),   # <O_L>_{|psi|^2} / ns
+                "Sq_chain": sq / n if n else sq, "Sq_psi2": sqz / z if z else sqz}
+
     # -- multi-GPU: NCCL sum of the accumulators inside the C ABI ----------------------------
     def comm_init_rank(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
         """collective over the ranks of a one-process-per-GPU job (kdsl_comm_init_rank)"""
@@ -591,6 +617,27 @@ def write_checkpoint(mc: MC, out) -> None:
     else:
         out["kappa_up"] = np.asarray(mc._kappa_up, dtype=np.int64)
         out["kappa_down"] = np.asarray(mc._kappa_down, dtype=np.int64)
+
+
+def save_checkpoint_npz(mc: MC, path: str, ctx: Optional[MCContext] = None) -> None:
+    """The checkpoint group as a file: `.npz` with the reference's dataset names and dtypes (`kappa_up`, `kappa_down`
+    Int64, src/MonteCarlo.jl:715-719) plus `rng_state` (uint64 [n_walkers, 4]) and, when a context is given, `sweeps`
+    (ctx.sweeps, which Carlo keeps in its own part of the HDF5 file).  libhdf5 is not in this image; the Julia side
+    (julia/KagomeDSLB200.jl) writes the same datasets into Carlo's HDF5 group."""
+    group: Dict[str, np.ndarray] = {}
+    write_checkpoint(mc, group)
+    if ctx is not None:
+        group["sweeps"] = np.asarray(ctx.sweeps, dtype=np.int64)
+    np.savez(path, **group)
+
+
+def load_checkpoint_npz(mc: MC, path: str, ctx: Optional[MCContext] = None, defer: bool = False) -> None:
+    """inverse of save_checkpoint_npz (`read_checkpoint!`, src/MonteCarlo.jl:751-755)"""
+    with np.load(path) as f:
+        group = {k: f[k] for k in f.files}
+    if ctx is not None and "sweeps" in group:
+        ctx.sweeps = int(group["sweeps"])
+    read_checkpoint_(mc, group, defer=defer)
 
 
 def read_checkpoint_(mc: MC, inp, defer: bool = False) -> None:

@@ -217,6 +217,14 @@ def getxprime(bonds, kup, kdn):
     return out
 
 
+def structure_factor(kup, cos_qr, sin_qr):
+    """S(q) = |sum_i exp(i q r_i) Sz_i|^2 / ns of one configuration (Sz_i = +1/2 where kappa_up[i] != 0, else -1/2);
+    checker of the product's extra observable (kdsl_set_observables), numpy"""
+    sz = np.where(np.asarray(kup) != 0, 0.5, -0.5)
+    re, im = np.asarray(cos_qr) @ sz, np.asarray(sin_qr) @ sz
+    return (re * re + im * im) / len(sz)
+
+
 class Xoshiro:
     """Julia's Random.Xoshiro stream (state supplied explicitly)."""
 

@@ -308,6 +308,63 @@ def test_exact_energy_12_sites(kd):
     assert err < 5e-4
 
 
+def test_reweighted_energy_is_the_psi2_average_12_sites(kd):
+    """The chain samples |psi|^2 / Z_mu; the Z_mu-reweighted estimator <O_L Z_mu> / <Z_mu> (kdsl_set_observables) must give
+    the |psi|^2 average instead: exact enumeration -0.3720882491 vs -0.3714938624 for the chain's own law (derived.json)."""
+    nw, therm, n = 2048, 2000, 12000
+    mc = kd.MC({"n1": 2, "n2": 2, "PBC": (False, False), "N_up": 6, "N_down": 6, "n_walkers": nw})
+    ctx = kd.MCContext({"thermalization": therm, "seed": 7, "binsize": 1})
+    kd.init_(mc, ctx, {"n1": 2, "n2": 2, "N_up": 6})
+    mc.engine.set_observables()
+    kd.run_(mc, ctx, therm + n)
+    obs = mc.engine.observables()
+    out, _, ol_w = mc.engine.accumulators(per_walker=True)
+    _, n_w = mc.engine.last_OL()
+    err = (ol_w / n_w / 12.0).std(ddof=1) / np.sqrt(nw)
+    assert obs["n"] == out[kd._lib.ACC_N_OL]
+    assert abs(obs["energy_psi2"] - (-0.3720882491)) < 6 * err + 2e-5, (obs["energy_psi2"], err)
+    assert abs(obs["energy_psi2"] - (-0.3714938624)) > 3 * err               # ... and it is NOT the chain-law value
+
+
+@pytest.mark.parametrize("variant", [3, 2, 0])
+def test_extra_observables_match_oracle(kd, variant):
+    """S(q) and the Z_mu-weighted sums taken at the :OL cadence equal the oracle-side evaluation (numpy structure factor,
+    oracle Z and getOL) on the same replayed chain"""
+    lat, ham = U.problem(4, 3)
+    ns, nw, n = kd.ns(lat), 6, 400
+    rng = np.random.default_rng(17)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=200.0)
+    r = rng.random((n, nw)) * 0.6
+    bond = rng.integers(1, len(ham.nn) + 1, size=(n, nw)).astype(np.int32)
+    coords = np.array([kd.get_site_coord(lat, s) for s in range(1, ns + 1)], dtype=np.float64)
+    qs = np.array([[0.0, 0.0], [np.pi, 0.0], [2 * np.pi / 3, 2 * np.pi / np.sqrt(3.0)], [0.3, -1.1]])
+    eng = kd.Engine(ham, nw)
+    eng.set_option("update_variant", variant)
+    eng.set_observables(qs, coords)
+    eng.set_config(ku, kdn)
+    eng.refresh()
+    eng.replay(r, bond, thermalization=0)
+    got = eng.observables()
+    cos_t, sin_t = np.cos(qs @ coords.T), np.sin(qs @ coords.T)
+    ref = np.zeros(4 + 2 * len(qs))
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
+        for s in range(n):
+            mc.sweep(replay=(r[s, w], int(bond[s, w]), 1))
+            mc.sweeps = mc.sweeps + 1
+            if mc.sweeps % (ns // 2) == 0:                                    # Carlo.measure! cadence (:630)
+                oku, okd = mc.kappa()
+                z, ol, sq = U.O.Z(ham.nn, oku, okd), mc.getOL(), U.O.structure_factor(oku, cos_t, sin_t)
+                ref[0] += 1; ref[1] += z; ref[2] += ol * z
+                ref[4:4 + len(qs)] += sq; ref[4 + len(qs):] += sq * z
+    assert got["n"] == ref[0] == nw * (n // (ns // 2))
+    assert got["sum_Z"] == ref[1]
+    assert abs(got["sum_OL_Z"] - ref[2]) <= 1e-10 * abs(ref[2])
+    assert np.allclose(got["sum_Sq"], ref[4:4 + len(qs)], rtol=1e-12, atol=1e-12)
+    assert np.allclose(got["sum_Sq_Z"], ref[4 + len(qs):], rtol=1e-12, atol=1e-10)
+    assert abs(got["Sq_chain"][0]) < 1e-12                                    # S(q = 0) = (sum Sz)^2 / ns = 0 at half filling
+    eng.close()
+
+
 def _run_chain(kd, ham, ku, kdn, states, n_sweeps, options):
     nw = ku.shape[0]
     eng = kd.Engine(ham, nw)

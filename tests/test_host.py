@@ -145,6 +145,17 @@ def test_checkpoint_roundtrip_and_evaluables():          # test-MonteCarlo.jl:50
     mc2 = kd.MC(params)
     kd.read_checkpoint_(mc2, group, defer=True)
     assert np.array_equal(mc2.kappa_up, mc._kappa_up) and np.array_equal(mc2.kappa_down, mc._kappa_down)
+    # the same group as a file (.npz with the reference's dataset names / dtypes, plus ctx.sweeps)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "run0001.npz")
+        c1 = kd.MCContext({"seed": 1}); c1.sweeps = 4321
+        kd.save_checkpoint_npz(mc, path, c1)
+        with np.load(path) as f:
+            assert f["kappa_up"].dtype == np.int64 and f["kappa_down"].dtype == np.int64 and int(f["sweeps"]) == 4321
+        mc3, c3 = kd.MC(params), kd.MCContext({"seed": 1})
+        kd.load_checkpoint_npz(mc3, path, c3, defer=True)
+        assert c3.sweeps == 4321 and np.array_equal(mc3.kappa_down, mc._kappa_down)
     ev = kd.Evaluator()
     kd.register_evaluables(kd.MC, ev, params)
     ctx = kd.MCContext({"binsize": 3, "seed": 123, "thermalization": 10})
