@@ -360,7 +360,8 @@ def run_ours(args):
     # per ACCEPTED move.
     if woodbury:
         n_units, unit_name = upd["flushes"], "walker flush"
-        kname = "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)"
+        kname = ("k_flush_c (delayed rank-k update of the ComplexF64 W, FP64 FMA, one thread per row)" if cplx else
+                 "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)")
         n_launch = max(upd["launches"] // 2, 1)
     else:
         n_units, unit_name = upd.get("moves", 0), "accepted move"
@@ -508,8 +509,7 @@ def run_ours(args):
 
     # ---- the reference-style immediate rank-1 W update (update_W!, src/MonteCarlo.jl:279-292) timed alone:
     #      every walker applies one move; 16 ns^2 algorithmic bytes per move ----
-    if not cplx:
-        eng.set_option("update_variant", 0)
+    eng.set_option("update_variant", 0)
     eng.reset_timers()
     eng.set_profiling(True)
     wl = np.arange(nw, dtype=np.int32)
@@ -524,8 +524,7 @@ def run_ours(args):
                       "moves_per_launch": t1["moves"] / max(t1["launches"], 1), "algorithmic_bytes_per_move": B_acc,
                       "note": "peak = the driver's measured COPY bandwidth (two address streams); this kernel is an in-place "
                               "read-modify-write over one stream and can slightly exceed it"}
-    if not cplx:
-        eng.set_option("update_variant", 2)
+    eng.set_option("update_variant", 2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -90,10 +90,11 @@ int kdsl_create(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_
  * src/Hamiltonian.jl:201-204, 325-327; scripts/LL.jl): U_up / U_dn are column-major Matrix{ComplexF64}, i.e.
  * interleaved (re, im) doubles [ns x N x 2].  Same entry points as the real engine; kdsl_get_W / kdsl_set_W then
  * move interleaved complex matrices (2 * ns * N doubles), the acceptance uses abs2(ratio) (src/MonteCarlo.jl:581)
- * and O_L is real(OL) (src/Hamiltonian.jl:777).  This mode runs the reference's own update algorithm on the GPU
- * (immediate rank-1 update per accepted move); reevaluateW! inverts tilde_U through its real 2N x 2N embedding on
- * the blocked DMMA kernels ("inverse_variant" 0 / 4 / 5; 1 = unblocked complex Gauss-Jordan).  kdsl_set_option
- * rejects the delayed-update options.  At most 512 orbitals per species.  kdsl_is_complex reports the kind of a handle.
+ * and O_L is real(OL) (src/Hamiltonian.jl:777).  The accepted-move updates are delayed in Woodbury form like in the
+ * real engine ("update_variant" 2, default: kdsl_woodbury_c.cuh; "flush_every" + "flush_threshold" <= 24) or applied
+ * immediately as the reference does ("update_variant" 0: rank-1 zgeru per accepted move); reevaluateW! inverts tilde_U
+ * through its real 2N x 2N embedding on the blocked DMMA kernels ("inverse_variant" 0 / 4 / 5; 1 = unblocked complex
+ * Gauss-Jordan).  At most 512 orbitals per species.  kdsl_is_complex reports the kind of a handle.
  */
 int kdsl_create_c128(kdsl_handle *out, int device, int ns, int n_up, int n_dn, int n_bonds,
                      const int32_t *bonds, const double *U_up, const double *U_dn, int n_walkers);

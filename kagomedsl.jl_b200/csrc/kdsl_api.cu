@@ -30,6 +30,7 @@
 #include "kdsl_resident.cuh"
 #include "kdsl_update.cuh"
 #include "kdsl_complex.cuh"
+#include "kdsl_woodbury_c.cuh"
 
 #define KDSL_VERSION_NUM 110
 #define KDSL_KTH 16          /* pending factors that trigger a flush */
@@ -192,6 +193,10 @@ struct Span {
 };
 
 int grid_for_warps(int nw) { return (nw * 32 + 255) / 256; }
+
+size_t measure_wb_smem_c(const DevState &S) {
+    return ((size_t)S.kmax * (S.n_up + S.n_dn) + 2 * (size_t)S.kmax * S.kmax) * 2 * sizeof(double) + 2 * S.kmax * sizeof(int);
+}
 
 size_t measure_wb_smem(const DevState &S) {
     return ((size_t)S.kmax * (S.n_up + S.n_dn) + 2 * (size_t)S.kmax * S.kmax) * sizeof(double) + 4 * S.kmax * sizeof(int);
@@ -487,6 +492,22 @@ int launch_flush(kdsl_handle h, bool all) {
     const DevState &S = h->S;
     const int *list = all ? nullptr : S.flush_list;
     int *cptr = all ? nullptr : S.cnt + 4;
+    if (h->cplx) {
+        // ComplexF64: FMA-pipe flush, one thread per row (kdsl_woodbury_c.cuh); kmax <= 24 (checked in kdsl_set_option)
+        const int Np = std::max(S.n_up, S.n_dn);
+        const size_t smem = (size_t)24 * Np * 2 * sizeof(double);
+        const int per_sm = 2 * (smem + 12 * 1024) <= (size_t)227 * 1024 ? 2 : 1;
+        {
+            Span sp(h, KDSL_T_UPDATE);
+            k_flush_c<24, 216><<<h->num_sms * per_sm, 224, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Np);
+            CK(cudaGetLastError());
+        }
+        k_flush_finish_wb<<<1, 1024, 0, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
+        CK(cudaGetLastError());
+        h->t_launch[KDSL_T_UPDATE] += 1;
+        h->since_flush = 0;
+        return KDSL_OK;
+    }
     if (h->update_variant == 2 && (h->flush_variant == 0 || h->flush_variant == 3)) {
         int rc = S.kmax <= 20 ? launch_flush_wb_kernel<20>(h, list, cptr)
                : S.kmax <= 24 ? launch_flush_wb_kernel<24>(h, list, cptr)
@@ -587,7 +608,14 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
         {
             Span sp(h, KDSL_T_PROPOSE);
             const size_t off = (size_t)s * S.nw;
-            if (woodbury) {
+            if (woodbury && h->cplx) {
+                if (replay)
+                    k_decide_wb_c<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, (int)g, h->rp_r + off, h->rp_bond + off,
+                                                                      have_pick ? h->rp_pick + off : nullptr);
+                else
+                    k_decide_wb_c<false><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, (int)g, nullptr, nullptr, nullptr);
+                CK(cudaGetLastError());
+            } else if (woodbury) {
                 if (replay)
                     k_decide_wb<true><<<pgrid, 256, 0, h->stream>>>(S, gate ? 1 : 0, (int)g, h->rp_r + off, h->rp_bond + off,
                                                                     have_pick ? h->rp_pick + off : nullptr);
@@ -640,7 +668,8 @@ int run_sweeps(kdsl_handle h, int64_t n, int64_t therm, bool replay, bool have_p
         s += g;
         if (therm >= 0 && h->sweeps > therm && (h->sweeps % S.n_occ) == 0) {   // :630 (post-increment)
             Span sp(h, KDSL_T_MEASURE);
-            if (woodbury) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, nullptr, 1);
+            if (woodbury && h->cplx) k_measure_wb_c<<<S.nw, 256, measure_wb_smem_c(S), h->stream>>>(S, nullptr, 1);
+            else if (woodbury) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, nullptr, 1);
 #ifdef KDSL_DEV_VARIANTS
             else if (delayed) k_measure_delayed<<<pgrid, 256, 0, h->stream>>>(S, nullptr, 1);
 #endif
@@ -755,7 +784,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
 
     kdsl_handle h = new kdsl_handle_s();
     h->cplx = cplx;
-    if (cplx) { h->update_variant = 0; h->inverse_variant = 0; }  // complex: the reference's rank-1 updates; inverse through the real embedding
+    if (cplx) { h->update_variant = 2; h->inverse_variant = 0; }  // complex: Woodbury delayed updates too; inverse through the real embedding
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     DevState &S = h->S;
@@ -811,13 +840,13 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     ALLOC(S.n_acc, nw); ALLOC(S.n_reach, nw); ALLOC(S.n_refresh, nw);
     ALLOC(S.ol_sum, nw); ALLOC(S.ol_sq, nw); ALLOC(S.ol_last, nw); ALLOC(S.ol_n, nw); ALLOC(S.upd_moves, 4);
     S.kmax = KDSL_KMAX; S.kth = KDSL_KTH;                  // (the buffers are sized for the largest kmax = 32)
-    const size_t kal = cplx ? 1 : KDSL_KALLOC;                    // (no delayed updates in complex mode)
-    ALLOC(S.facA_up, nw * kal * ns); ALLOC(S.facA_dn, nw * kal * ns);
+    const size_t kal = KDSL_KALLOC;
+    ALLOC(S.facA_up, cz * nw * kal * ns); ALLOC(S.facA_dn, cz * nw * kal * ns);
 #ifdef KDSL_DEV_VARIANTS
     ALLOC(S.facB_up, nw * kal * ((n_up + 7) / 8 * 8)); ALLOC(S.facB_dn, nw * kal * ((n_dn + 7) / 8 * 8));
 #endif
     ALLOC(S.fcnt, 2 * nw); ALLOC(S.flush_list, nw); ALLOC(S.listed, nw);
-    ALLOC(S.wbT, 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
+    ALLOC(S.wbT, cz * 2 * nw * KDSL_KALLOC * KDSL_KALLOC); ALLOC(S.wbK, 2 * nw * KDSL_KALLOC); ALLOC(S.wbL, 2 * nw * KDSL_KALLOC);
     h->Gstride = (size_t)((std::max(n_up, n_dn) + 7) / 8 * 8) * KDSL_KALLOC;   // (Gbuf itself is allocated when flush_variant 3 is chosen)
     if (cplx) {
         // the refresh workspace holds the real embedding [[X, -Y], [Y, X]] of tilde_U, padded: Np = roundup(2 N, 8)
@@ -885,6 +914,20 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     // Opt-in dynamic shared memory of the Woodbury kernels.  cudaFuncSetAttribute is per device (context), so this is
     // done for every handle, not once per process; the sizes are validated against the device limit here and in
     // kdsl_set_option ("flush_every" / "flush_threshold" change kmax).
+    if (cplx) {
+        cudaFuncAttributes fa;
+        CKD(cudaFuncGetAttributes(&fa, (const void *)k_measure_wb_c));
+        h->smem_optin = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+        CKD(cudaFuncSetAttribute(k_measure_wb_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        CKD(cudaFuncGetAttributes(&fa, (const void *)k_flush_c<24, 216>));
+        CKD(cudaFuncSetAttribute(k_flush_c<24, 216>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        const size_t need_f = (size_t)24 * std::max(n_up, n_dn) * 2 * sizeof(double);
+        if (measure_wb_smem_c(S) > h->smem_optin || need_f + fa.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) {
+            // too large for the Woodbury kernels' shared memory: the reference's immediate rank-1 update (any size)
+            h->update_variant = 0;
+        }
+    }
     if (!cplx) {
         // the largest dynamic allocation a kernel may ask for = the device's opt-in limit minus its static shared memory
         auto optin_dynamic = [&](const void *func, size_t *out) -> cudaError_t {
@@ -1127,7 +1170,8 @@ int kdsl_measure(kdsl_handle h, double *ol) {
     const DevState &S = h->S;
     {
         Span sp(h, KDSL_T_MEASURE);
-        if (h->cplx) k_measure_c<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
+        if (h->cplx && h->update_variant == 2) k_measure_wb_c<<<S.nw, 256, measure_wb_smem_c(S), h->stream>>>(S, h->d_tmp_d, 0);
+        else if (h->cplx) k_measure_c<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, h->d_tmp_d, 0);
         else if (h->update_variant == 2) k_measure_wb<<<S.nw, 256, measure_wb_smem(S), h->stream>>>(S, h->d_tmp_d, 0);
         // (update_variant 0 and 3 keep W itself up to date: the plain kernel below)
 #ifdef KDSL_DEV_VARIANTS
@@ -1343,9 +1387,12 @@ int kdsl_reset_timers(kdsl_handle h) {
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (h && h->cplx && name) {
         const std::string nm(name);
-        if ((nm == "update_variant" && value != 0) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5) || nm == "flush_every" ||
-            nm == "flush_threshold")
-            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (rank-1 updates; inverse_variant 0/4/5 = real-embedding blocked inverse, 1 = unblocked complex)", name, (long long)value);
+        if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5) ||
+            nm == "flush_variant")
+            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; inverse_variant 0/4/5 = real-embedding blocked inverse, 1 = unblocked complex)", name, (long long)value);
+        if (nm == "update_variant" && value == 2 && measure_wb_smem_c(h->S) > h->smem_optin)
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "the ComplexF64 Woodbury kernels need %zu bytes of shared memory at ns = %d (device limit %zu)",
+                        measure_wb_smem_c(h->S), h->S.ns, h->smem_optin);
     }
     if (!h || !name) return fail(KDSL_ERR_INVALID_ARGUMENT, "null argument");
     const std::string n(name);
@@ -1406,12 +1453,12 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
         if (h->update_variant != 2) return fail(KDSL_ERR_STATE, "%s applies to update_variant 2 only", name);
         const int fe = n == "flush_every" ? (int)value : h->flush_every;
         const int kth = n == "flush_threshold" ? (int)value : h->S.kth;
-        if (fe < 1 || kth < 1 || fe + kth > KDSL_KALLOC)
-            return fail(KDSL_ERR_INVALID_ARGUMENT, "need flush_every >= 1, flush_threshold >= 1 and their sum <= %d", KDSL_KALLOC);
+        if (fe < 1 || kth < 1 || fe + kth > (h->cplx ? 24 : KDSL_KALLOC))
+            return fail(KDSL_ERR_INVALID_ARGUMENT, "need flush_every >= 1, flush_threshold >= 1 and their sum <= %d", h->cplx ? 24 : KDSL_KALLOC);
         {
             DevState T = h->S;
             T.kmax = fe + kth;
-            if (measure_wb_smem(T) > h->smem_optin)
+            if ((h->cplx ? measure_wb_smem_c(T) : measure_wb_smem(T)) > h->smem_optin)
                 return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_every + flush_threshold = %d needs %zu bytes of shared memory in k_measure_wb at ns = %d (device limit %zu)",
                             fe + kth, measure_wb_smem(T), T.ns, h->smem_optin);
         }

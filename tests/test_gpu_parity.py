@@ -495,23 +495,28 @@ def test_complex_refresh_update_measure_match_oracle(kd, n1, n2, B):
         assert U.relerr(eng.get_W(w, 0), Wu2) < TOL
         assert U.relerr(eng.get_W(w, 1), Wd2) < TOL
     with pytest.raises(kd.KdslError):
-        eng.set_option("update_variant", 2)                                 # delayed updates are real-only for now
+        eng.set_option("flush_variant", 3)                                  # the bulk-async flush is real-only
     eng.close()
 
 
-def test_complex_replay_and_device_rng_match_oracle(kd):
+@pytest.mark.parametrize("variant", [2, 0])
+def test_complex_replay_and_device_rng_match_oracle(kd, variant):
     """ComplexF64 chain: replayed proposals -> kappa / Z_mu / counters bit-exact, W within 1e-10; device Xoshiro ->
-    same trajectory, counters and O_L sums as the oracle's Carlo loop."""
+    same trajectory, counters and O_L sums as the oracle's Carlo loop.  variant 2 = Woodbury delayed updates (default),
+    0 = the reference's immediate rank-1 update."""
     lat, ham = _complex_problem(kd, 4, 3, 0.37)
     ns, nw, n_sweeps = kd.ns(lat), 6, 900
     rng = np.random.default_rng(8)
     ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=300.0)
     r = rng.random((n_sweeps, nw))
+    r[:, 3:] *= 0.45                                                        # more acceptances: pending updates, flushes
     bond = rng.integers(1, len(ham.nn) + 1, size=(n_sweeps, nw)).astype(np.int32)
     eng = kd.Engine(ham, nw)
+    eng.set_option("update_variant", variant)
     eng.set_config(ku, kdn)
     eng.refresh()
     eng.replay(r, bond)
+    ol = eng.measure()                                                      # (Woodbury form: pending updates included)
     orc = U.oracle_walkers(ham, ku, kdn, dtype="c128")
     gku, gkd = eng.get_config()
     z, zr = eng.Z()
@@ -521,6 +526,7 @@ def test_complex_replay_and_device_rng_match_oracle(kd):
             mc.sweeps = mc.sweeps + 1
         oku, okd = mc.kappa()
         assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd)
+        assert abs(ol[w] - mc.getOL()) <= TOL * max(1.0, abs(mc.getOL()))
         assert z[w] == zr[w] == U.O.Z(ham.nn, oku, okd)
         Wu, Wd = mc.W()
         assert U.relerr(eng.get_W(w, 0), Wu) < TOL and U.relerr(eng.get_W(w, 1), Wd) < TOL
@@ -531,6 +537,7 @@ def test_complex_replay_and_device_rng_match_oracle(kd):
     # device RNG
     states = kd.walker_states(3, nw)
     eng = kd.Engine(ham, nw)
+    eng.set_option("update_variant", variant)
     eng.set_config(ku, kdn)
     eng.set_rng(states)
     eng.refresh()
