@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libkdsl.so")
+SO_PATH = os.environ.get("KDSL_LIB") or os.path.join(CSRC, "libkdsl.so")   # KDSL_LIB: developer builds (make libkdsl_ticks.so)
 
 KDSL_OK = 0
 KDSL_ERR_INVALID_ARGUMENT = -1

@@ -20,6 +20,7 @@
 #include "kdsl_refresh_fast.cuh"
 #include "kdsl_inverse_v4.cuh"
 #include "kdsl_inverse_v5.cuh"
+#include "kdsl_inverse_cl.cuh"
 #include "kdsl_reeval_fused.cuh"
 #ifdef KDSL_DEV_VARIANTS   // superseded kernels kept for A/B measurements: `make DEV=1` (not in the product library)
 #include "kdsl_inverse_v3.cuh"
@@ -115,6 +116,10 @@ struct kdsl_handle_s {
     int flush_every = KDSL_FLUSH_EVERY;   // sweeps between flush launches (kmax = kth + flush_every <= 32)
     int fuse_sweeps = 1;          // fuse consecutive proposals into one launch where the loop allows it
     int inverse_tuning = 0;
+    int inverse_cluster = 4;      // CTAs per matrix of k_inverse_cl (256 < Np <= 512): 1 P + (n - 1) G; 0 = one CTA per matrix (k_inverse_v4)
+    int inverse_rs = 8;           // row slices per column-tile group of its trailing update
+    double *cl_scratch = nullptr; // per-cluster exchange buffers of k_inverse_cl
+    int cl_scratch_clusters = 0;
     int update_ch = 8;
     // profiling
     bool profiling = false;
@@ -262,6 +267,40 @@ int launch_inverse_v5(kdsl_handle h, const int *list, double *A, int spin, int N
     return KDSL_OK;
 }
 
+// Both species in one launch of the cluster kernel (kdsl_inverse_cl.cuh); returns -1 when it does not apply.
+int launch_inverse_cl(kdsl_handle h, const int *list) {
+    const int NpMax = std::max(h->Np_up, h->Np_dn), NpMin = std::min(h->Np_up, h->Np_dn);
+    const int cl = h->inverse_cluster;
+    if (!(h->inverse_variant == 0 || h->inverse_variant == 7) || cl < 2 || cl > 8 || NpMax > 512 || NpMin < 8) return -1;
+    if (h->inverse_variant == 0 && NpMax <= 256) return -1;
+    constexpr int NB = 24, CT = 2;
+    const size_t smem = inverse_cl_smem(NB, NpMax);
+    if (smem > (size_t)227 * 1024) return -1;
+    auto kern = k_inverse_cl<NB, CT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cl * (h->num_sms / cl));
+    int ncl = 0;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) return -1;
+    ncl = std::min(ncl, h->num_sms / cl);
+    if (getenv("KDSL_DEBUG_OCC")) fprintf(stderr, "k_inverse_cl: cluster size %d, %d active clusters, smem %zu\n", cl, ncl, smem);
+    if (!h->cl_scratch || h->cl_scratch_clusters < ncl) {
+        int rc = dev_alloc(h, &h->cl_scratch, (size_t)ncl * inverse_cl_scratch_doubles(NB, NpMax));
+        if (rc) return rc;
+        h->cl_scratch_clusters = ncl;
+    }
+    cfg.gridDim = dim3(cl * ncl);
+    const int cs = NpMax, rs = std::max(1, h->inverse_rs);
+    CK(cudaLaunchKernelEx(&cfg, kern, h->S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs, h->cl_scratch, rs));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     if ((h->inverse_variant == 0 || h->inverse_variant == 5) && Np <= 256) {
         // look-ahead version: pivot loop of panel s+1 concurrent with the DMMA update of step s
@@ -324,9 +363,12 @@ int launch_refresh(kdsl_handle h, const int *list) {
         }
         {
             Span sp(h, KDSL_T_REFRESH_INVERSE);
-            int rc = launch_inverse(h, list, h->A_up, 0, h->Np_up);
-            if (rc) return rc;
-            rc = launch_inverse(h, list, h->A_dn, 1, h->Np_dn);
+            int rc = launch_inverse_cl(h, list);
+            if (rc < 0) {
+                rc = launch_inverse(h, list, h->A_up, 0, h->Np_up);
+                if (rc) return rc;
+                rc = launch_inverse(h, list, h->A_dn, 1, h->Np_dn);
+            }
             if (rc) return rc;
             k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
             CK(cudaGetLastError());
@@ -407,9 +449,12 @@ int launch_refresh(kdsl_handle h, const int *list) {
     {
         Span sp(h, KDSL_T_REFRESH_INVERSE);
         if (fast) {
-            int rc = launch_inverse(h, list, h->A_up, 0, h->Np_up);
-            if (rc) return rc;
-            rc = launch_inverse(h, list, h->A_dn, 1, h->Np_dn);
+            int rc = launch_inverse_cl(h, list);
+            if (rc < 0) {
+                rc = launch_inverse(h, list, h->A_up, 0, h->Np_up);
+                if (rc) return rc;
+                rc = launch_inverse(h, list, h->A_dn, 1, h->Np_dn);
+            }
             if (rc) return rc;
         } else {
             const size_t smem = (size_t)Nmax * (2 * sizeof(double) + sizeof(int));
@@ -1387,9 +1432,9 @@ int kdsl_reset_timers(kdsl_handle h) {
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (h && h->cplx && name) {
         const std::string nm(name);
-        if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5) ||
+        if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5 && value != 7) ||
             nm == "flush_variant")
-            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; inverse_variant 0/4/5 = real-embedding blocked inverse, 1 = unblocked complex)", name, (long long)value);
+            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; inverse_variant 0/4/5/7 = real-embedding blocked inverse, 1 = unblocked complex)", name, (long long)value);
         if (nm == "update_variant" && value == 2 && measure_wb_smem_c(h->S) > h->smem_optin)
             return fail(KDSL_ERR_INVALID_ARGUMENT, "the ComplexF64 Woodbury kernels need %zu bytes of shared memory at ns = %d (device limit %zu)",
                         measure_wb_smem_c(h->S), h->S.ns, h->smem_optin);
@@ -1432,7 +1477,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
 #ifndef KDSL_DEV_VARIANTS
         if (value == 2 || value == 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
 #endif
-        if (value < 0 || value > 6) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5 or 6");
+        if (value < 0 || value > 7) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5, 6 or 7");
         h->inverse_variant = (int)value;
     }
     else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;
@@ -1482,6 +1527,14 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     else if (n == "fused_ctas") h->fused_ctas = (int)value;
     else if (n == "flush_dbg") h->flush_dbg = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
+    else if (n == "inverse_cluster") {
+        if (value != 0 && (value < 2 || value > 8)) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_cluster must be 0 (one CTA per matrix) or 2..8 CTAs per matrix");
+        h->inverse_cluster = (int)value;
+    }
+    else if (n == "inverse_row_slices") {
+        if (value < 1 || value > 64) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_row_slices must be 1..64");
+        h->inverse_rs = (int)value;
+    }
     else return fail(KDSL_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
     return KDSL_OK;
 }
@@ -1513,8 +1566,8 @@ int kdsl_debug_inverse_phases(kdsl_handle h, long long *out) {
     int rc = use_device(h);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpyFromSymbol(out, g_inv_phase_cycles, 8 * sizeof(long long)));
-    long long z[8] = {0};
+    CK(cudaMemcpyFromSymbol(out, g_inv_phase_cycles, 16 * sizeof(long long)));   // out: 16 entries
+    long long z[16] = {0};
     CK(cudaMemcpyToSymbol(g_inv_phase_cycles, z, sizeof z));
     return KDSL_OK;
 }

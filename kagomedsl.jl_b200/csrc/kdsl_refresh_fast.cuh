@@ -81,7 +81,7 @@ k_gather_tilde_padded(DevState S, const int *__restrict__ list, double *__restri
 // developer instrumentation (build with -DKDSL_PHASE_TICKS): SM cycles spent by CTA 0 in each phase of the
 // re-evaluation kernels.  Compiled out of the product library.
 #ifdef KDSL_PHASE_TICKS
-__device__ long long g_inv_phase_cycles[8];
+__device__ long long g_inv_phase_cycles[16];   // [8..15]: k_inverse_cl
 #define PHASE_CLOCK() clock64()
 #define PHASE_TICK_AT(idx, thr)                                          \
     do {                                                                 \

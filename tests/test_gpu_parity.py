@@ -47,10 +47,10 @@ def test_refresh_matches_oracle(kd, n1, n2, PBC, anti, flux):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6, 7])
 def test_refresh_imbalanced_filling_and_variants(kd, variant):
     """N_up != N_down (scripts/FP.jl), N not a multiple of 8; fused re-evaluation (0 / 6), simple kernels (1),
-    gather + blocked DMMA inverse + product (4 / 5)"""
+    gather + blocked DMMA inverse + product (4 / 5), cluster inverse (7)"""
     lat, ham = U.problem(4, 3, N_up=20)
     ns, nw = kd.ns(lat), 5
     rng = np.random.default_rng(21)
@@ -63,6 +63,58 @@ def test_refresh_imbalanced_filling_and_variants(kd, variant):
         Wu, Wd = mc.W()
         assert U.relerr(eng.get_W(w, 0), Wu) < TOL
         assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("n,N_up,cluster,row_slices,nw", [
+    (6, None, 4, 8, 90), (6, 50, 2, 1, 20), (8, None, 4, 8, 50), (8, 90, 5, 3, 50), (8, None, 8, 2, 24), (8, None, 3, 64, 24)])
+def test_cluster_inverse_matches_oracle(kd, n, N_up, cluster, row_slices, nw):
+    """k_inverse_cl (one matrix per thread-block cluster: 1 pivot CTA + cluster-1 update CTAs; the default for
+    256 < Np <= 512, selected here on small lattices by inverse_variant 7): several panels of 24 columns incl. a
+    partial last one, more (walker, species) items than resident clusters, all cluster sizes' work splits"""
+    lat, ham = U.problem(n, n, N_up=N_up)
+    ns = kd.ns(lat)
+    rng = np.random.default_rng(100 + n + cluster)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
+    eng = kd.Engine(ham, nw)
+    eng.set_option("inverse_variant", 7)
+    eng.set_option("inverse_cluster", cluster)
+    eng.set_option("inverse_row_slices", row_slices)
+    eng.set_config(ku, kdn)
+    for rep in range(2):                                         # the second pass reuses the per-cluster scratch buffers
+        eng.set_W(0, 0, np.zeros((ns, ham.N_up)))
+        eng.refresh()
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+    assert eng.accumulators()[kd._lib.ACC_N_SINGULAR] == 0
+    eng.close()
+
+
+def test_cluster_inverse_singular_matrix_is_flagged(kd):
+    """a singular tilde_U inside a batch of the cluster inverse: that walker is flagged, the clusters go on with the
+    other items (the singular flag travels through the per-cluster scratch: every CTA leaves the item at the same step)"""
+    lat, ham = U.problem(6, 6)
+    ns, nw = kd.ns(lat), 45
+    rng = np.random.default_rng(77)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
+    Ud = np.array(ham.U_down, dtype=np.float64).copy()
+    bad_sites = np.nonzero(kdn[7])[0]
+    Ud[bad_sites[0], :] = 0.0                                     # walker 7 (and whoever shares the site): a zero row in tilde_U_down
+    ham2 = kd.Hamiltonian(ham.N_up, ham.N_down, ham.U_up, Ud, ham.H_mat, ham.nn)
+    expect_bad = np.array([kdn[w, bad_sites[0]] != 0 for w in range(nw)])
+    assert expect_bad[7] and not expect_bad.all()
+    eng = kd.Engine(ham2, nw)
+    eng.set_option("inverse_variant", 7)
+    eng.set_config(ku, kdn)
+    with pytest.raises(kd.SingularException):
+        eng.refresh()
+    fl = eng.flags()
+    assert np.array_equal((fl & 1) != 0, expect_bad)
+    for w in np.nonzero(~expect_bad)[0][:6]:
+        Wd_ref = Ud @ np.linalg.inv(kd.tilde_U(Ud, kdn[w]))
+        assert U.relerr(eng.get_W(int(w), 1), Wd_ref) < 1e-8
     eng.close()
 
 
@@ -470,7 +522,7 @@ def test_complex_refresh_update_measure_match_oracle(kd, n1, n2, B):
     orc = U.oracle_walkers(ham, ku, kdn, dtype="c128")
     # inverse_variant 0 (default): inverse through the real 2N x 2N embedding on the blocked DMMA kernels;
     # 1: the reference-style unblocked complex Gauss-Jordan
-    for variant in (1, 5, 0):
+    for variant in (1, 5, 7, 0):
         eng.set_option("inverse_variant", variant)
         eng.set_W(0, 0, np.zeros_like(np.asarray(orc[0].W()[0])))           # make sure the refresh really rewrites W
         eng.refresh()

@@ -16,7 +16,7 @@ eng.sweep(2 * ns, -1)                       # decorrelate the walkers
 eng.set_option('inverse_variant', 1); eng.refresh()
 ws = [0, 3, nw - 1]
 W_ref = [(eng.get_W(w, 0).copy(), eng.get_W(w, 1).copy()) for w in ws]
-out = (C.c_longlong * 8)()
+out = (C.c_longlong * 16)()
 ctas = int(os.environ.get("FUSED_CTAS", "0"))
 eng.set_option("fused_ctas", ctas)
 for variant, tuning in [(5, 0)] + [(6, t) for t in tunings]:

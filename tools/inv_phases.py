@@ -8,7 +8,7 @@ lat = kd.DoubleKagome(1.0, n, n, (True, True), (True, False)); ns = kd.ns(lat)
 ham = kd.Hamiltonian(ns // 2, ns // 2, lat); ku, kdn = kd.init_conf_qr(ham, ns, ns // 2)
 eng = kd.Engine(ham, nw, 0); eng.set_option('inverse_variant', 1); eng.set_config(ku, kdn); eng.refresh()
 W_ref = eng.get_W(3, 1).copy()
-out = (C.c_longlong * 8)()
+out = (C.c_longlong * 16)()
 names = ["1 panel load", "2 panel LU", "3 publish+moves", "4 columns (U_K, pivot rows)", "5 panel cols", "6 GEMM update"]
 # (variant 0 = k_inverse_v4 has four phases: load, pivot loop, publish + gather, GEMM update)
 eng.set_option('gemm_variant', 1)
