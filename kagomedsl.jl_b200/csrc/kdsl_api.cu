@@ -21,6 +21,7 @@
 #include "kdsl_inverse_v4.cuh"
 #include "kdsl_inverse_v5.cuh"
 #include "kdsl_inverse_cl.cuh"
+#include "kdsl_reeval_cl.cuh"
 #include "kdsl_reeval_fused.cuh"
 #ifdef KDSL_DEV_VARIANTS   // superseded kernels kept for A/B measurements: `make DEV=1` (not in the product library)
 #include "kdsl_inverse_v3.cuh"
@@ -120,6 +121,13 @@ struct kdsl_handle_s {
     int inverse_rs = 8;           // row slices per column-tile group of its trailing update
     double *cl_scratch = nullptr; // per-cluster exchange buffers of k_inverse_cl
     int cl_scratch_clusters = 0;
+    // cluster re-evaluation k_reeval_cl (256 < Np <= 512, real engine): one kernel, one matrix per cluster
+    bool rcl_ok = false;          // UT_up / UT_dn are built and the sizes fit
+    int rcl_NpMax = 0, rcl_CpMax = 0, rcl_nvtMax = 0, rcl_ntcMax = 0;
+    double *rcl_scratch = nullptr;   // per-cluster row-major workspace + exchange buffers
+    int rcl_scratch_clusters = 0;
+    int reeval_cluster = 4;       // CTAs per matrix of k_reeval_cl: 1 P + (n - 1) G
+    int reeval_rs = 4;            // row slices per column-tile pair of its trailing update
     int update_ch = 8;
     // profiling
     bool profiling = false;
@@ -301,6 +309,47 @@ int launch_inverse_cl(kdsl_handle h, const int *list) {
     return KDSL_OK;
 }
 
+// reevaluateW! as ONE cluster kernel (kdsl_reeval_cl.cuh); returns -1 when it does not apply.
+int launch_reeval_cl(kdsl_handle h, const int *list) {
+    if (!h->rcl_ok || h->cplx) return -1;
+    const int cl = h->reeval_cluster;
+    if (cl < 2 || cl > 8) return -1;
+    constexpr int NB = 24, DG = 4;
+    const int NG = cl - 1;
+    // X slots (column tiles) a CTA needs: its pairs of the first block step, its V tiles of the last step, one panel
+    const int pairs0 = (h->rcl_ntcMax + 1) / 2;
+    const int XT = std::max(std::max(2 * ((pairs0 + NG - 1) / NG), (h->rcl_nvtMax + cl - 1) / cl + 1), NB / 8);
+    const int nv = (h->rcl_nvtMax + cl - 1) / cl + 1;
+    if (nv > 32) return -1;                               // 16 warps x 2 column tiles in the last step
+    const int SW = 8 * nv;
+    const size_t smem = reeval_cl_smem(NB, h->rcl_NpMax, h->rcl_CpMax, h->S.ns, XT, SW);
+    if (smem > (size_t)227 * 1024) return -1;
+    auto kern = k_reeval_cl<NB, DG>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cl * (h->num_sms / cl));
+    int ncl = 0;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) return -1;
+    ncl = std::min(ncl, h->num_sms / cl);
+    if (getenv("KDSL_DEBUG_OCC")) fprintf(stderr, "k_reeval_cl: cluster size %d, %d active clusters, smem %zu, XT %d\n", cl, ncl, smem, XT);
+    if (!h->rcl_scratch || h->rcl_scratch_clusters < ncl) {
+        int rc = dev_alloc(h, &h->rcl_scratch, (size_t)ncl * reeval_cl_scratch_doubles(NB, h->rcl_NpMax, h->rcl_CpMax));
+        if (rc) return rc;
+        h->rcl_scratch_clusters = ncl;
+    }
+    cfg.gridDim = dim3(cl * ncl);
+    const int rs = std::max(1, h->reeval_rs);
+    CK(cudaLaunchKernelEx(&cfg, kern, h->S, list, h->rcl_scratch, (const double *)h->UT_up, (const double *)h->UT_dn, h->status,
+                          h->Np_up, h->Np_dn, h->rcl_NpMax, h->rcl_CpMax, XT, SW, rs));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     if ((h->inverse_variant == 0 || h->inverse_variant == 5) && Np <= 256) {
         // look-ahead version: pivot loop of panel s+1 concurrent with the DMMA update of step s
@@ -432,6 +481,17 @@ int launch_refresh(kdsl_handle h, const int *list) {
         else KDSL_FUSED_LAUNCH(24, 2, 6);
 #undef KDSL_FUSED_LAUNCH
         CK(cudaGetLastError());
+        k_refresh_status_fused<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
+        CK(cudaGetLastError());
+        h->t_launch[KDSL_T_REFRESH_INVERSE] += 1;
+        return KDSL_OK;
+    }
+    if (h->inverse_variant == 8 && h->rcl_ok) {
+        // one cluster kernel for 256 < Np <= 512 (kdsl_reeval_cl.cuh)
+        Span sp(h, KDSL_T_REFRESH_INVERSE);
+        int rc = launch_reeval_cl(h, list);
+        if (rc > 0) return rc;
+        if (rc < 0) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant 8 (cluster re-evaluation) does not fit this problem / reeval_cluster");
         k_refresh_status_fused<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
         CK(cudaGetLastError());
         h->t_launch[KDSL_T_REFRESH_INVERSE] += 1;
@@ -941,6 +1001,23 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaStreamSynchronize(h->stream));
         }
+    }
+    if (!cplx && std::max(h->Np_up, h->Np_dn) <= 512 && std::min(h->Np_up, h->Np_dn) >= 8) {
+        // cluster re-evaluation (k_reeval_cl; the default for 256 < Np <= 512, inverse_variant 8 forces it on smaller lattices):
+        // transposed U with padding rows (shared with k_reeval_fused); the workspaces are allocated at the first launch
+        const int Mp_up = (ns - n_up + 7) / 8 * 8, Mp_dn = (ns - n_dn + 7) / 8 * 8;
+        h->rcl_NpMax = std::max(h->Np_up, h->Np_dn);
+        h->rcl_CpMax = std::max(h->Np_up + Mp_up, h->Np_dn + Mp_dn);
+        h->rcl_nvtMax = std::max(Mp_up, Mp_dn) / 8;
+        h->rcl_ntcMax = h->rcl_CpMax / 8;
+        if (!h->UT_up) {
+            ALLOC(h->UT_up, (size_t)(ns + 9) * h->Np_up); ALLOC(h->UT_dn, (size_t)(ns + 9) * h->Np_dn);
+            k_build_UT<<<64, 256, 0, h->stream>>>(dUu, h->UT_up, ns, n_up, h->Np_up);
+            k_build_UT<<<64, 256, 0, h->stream>>>(dUd, h->UT_dn, ns, n_dn, h->Np_dn);
+            CKD(cudaGetLastError());
+            CKD(cudaStreamSynchronize(h->stream));
+        }
+        h->rcl_ok = true;
     }
 #undef ALLOC
     // default xoshiro states must not be all-zero: seed walker w with a fixed SplitMix64 stream
@@ -1477,7 +1554,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
 #ifndef KDSL_DEV_VARIANTS
         if (value == 2 || value == 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
 #endif
-        if (value < 0 || value > 7) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5, 6 or 7");
+        if (value < 0 || value > 8) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5, 6, 7 or 8");
         h->inverse_variant = (int)value;
     }
     else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;
@@ -1527,6 +1604,14 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     else if (n == "fused_ctas") h->fused_ctas = (int)value;
     else if (n == "flush_dbg") h->flush_dbg = (int)value;
     else if (n == "inverse_tuning") h->inverse_tuning = (int)value;
+    else if (n == "reeval_cluster") {
+        if (value < 2 || value > 8) return fail(KDSL_ERR_INVALID_ARGUMENT, "reeval_cluster must be 2..8 CTAs per matrix");
+        h->reeval_cluster = (int)value;
+    }
+    else if (n == "reeval_rs") {
+        if (value < 1 || value > 16) return fail(KDSL_ERR_INVALID_ARGUMENT, "reeval_rs must be 1..16");
+        h->reeval_rs = (int)value;
+    }
     else if (n == "inverse_cluster") {
         if (value != 0 && (value < 2 || value > 8)) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_cluster must be 0 (one CTA per matrix) or 2..8 CTAs per matrix");
         h->inverse_cluster = (int)value;

@@ -373,6 +373,7 @@ k_inverse_cl(DevState S, const int *__restrict__ list, double *__restrict__ A_up
 #ifdef KDSL_PHASE_TICKS
         if (blockIdx.x == 0 && tid == 0) g_inv_phase_cycles[15] += 1;
 #endif
+        if (sing) cl_sync();                            // nobody re-reads the flag after P has moved on to the next item
         // ---- index map for the consumer: colsrc[i] = elimination step at which row i was the pivot ----
         if (has_row && !sing) colsrc_base[((size_t)2 * b + spin) * cs_stride + tid] = gstep;
     }

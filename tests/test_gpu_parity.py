@@ -92,7 +92,35 @@ def test_cluster_inverse_matches_oracle(kd, n, N_up, cluster, row_slices, nw):
     eng.close()
 
 
-def test_cluster_inverse_singular_matrix_is_flagged(kd):
+@pytest.mark.parametrize("n1,n2,N_up,cluster,row_slices,nw", [
+    (6, 6, None, 4, 4, 90), (6, 6, 50, 2, 1, 20), (8, 8, None, 4, 4, 50), (8, 8, 90, 5, 3, 50), (8, 8, None, 8, 2, 24),
+    (8, 8, None, 3, 16, 24), (4, 3, 20, 4, 4, 40), (4, 3, None, 2, 4, 9)])
+def test_cluster_reeval_matches_oracle(kd, n1, n2, N_up, cluster, row_slices, nw):
+    """k_reeval_cl (the whole of reevaluateW! in one kernel, one matrix per thread-block cluster; the default for
+    256 < Np <= 512, forced here on small lattices by inverse_variant 8): single-panel matrices (first step = last step),
+    partial last panels, N_up != N_down, more items than resident clusters, every cluster size's work split"""
+    lat, ham = U.problem(n1, n2, N_up=N_up)
+    ns = kd.ns(lat)
+    rng = np.random.default_rng(300 + n1 + cluster)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
+    eng = kd.Engine(ham, nw)
+    eng.set_option("inverse_variant", 8)
+    eng.set_option("reeval_cluster", cluster)
+    eng.set_option("reeval_rs", row_slices)
+    eng.set_config(ku, kdn)
+    for rep in range(2):                                         # the second pass reuses the per-cluster workspaces
+        eng.set_W(0, 0, np.zeros((ns, ham.N_up)))
+        eng.refresh()
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn)):
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+    assert eng.accumulators()[kd._lib.ACC_N_SINGULAR] == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", [7, 8])
+def test_cluster_inverse_singular_matrix_is_flagged(kd, variant):
     """a singular tilde_U inside a batch of the cluster inverse: that walker is flagged, the clusters go on with the
     other items (the singular flag travels through the per-cluster scratch: every CTA leaves the item at the same step)"""
     lat, ham = U.problem(6, 6)
@@ -106,7 +134,7 @@ def test_cluster_inverse_singular_matrix_is_flagged(kd):
     expect_bad = np.array([kdn[w, bad_sites[0]] != 0 for w in range(nw)])
     assert expect_bad[7] and not expect_bad.all()
     eng = kd.Engine(ham2, nw)
-    eng.set_option("inverse_variant", 7)
+    eng.set_option("inverse_variant", variant)
     eng.set_config(ku, kdn)
     with pytest.raises(kd.SingularException):
         eng.refresh()
