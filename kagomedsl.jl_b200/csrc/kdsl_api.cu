@@ -22,6 +22,7 @@
 #include "kdsl_inverse_v5.cuh"
 #include "kdsl_inverse_cl.cuh"
 #include "kdsl_reeval_cl.cuh"
+#include "kdsl_inverse_cl_c.cuh"
 #include "kdsl_reeval_fused.cuh"
 #ifdef KDSL_DEV_VARIANTS   // superseded kernels kept for A/B measurements: `make DEV=1` (not in the product library)
 #include "kdsl_inverse_v3.cuh"
@@ -127,6 +128,10 @@ struct kdsl_handle_s {
     double *rcl_scratch = nullptr;   // per-cluster row-major workspace + exchange buffers
     int rcl_scratch_clusters = 0;
     int reeval_cluster = 4;       // CTAs per matrix of k_reeval_cl: 1 P + (n - 1) G
+    // ComplexF64 engine: complex cluster inverse on split (re, im) planes (k_inverse_cl_c)
+    int Npc_up = 0, Npc_dn = 0;   // complex tilde_U dimensions padded to a multiple of 8
+    double *clc_scratch = nullptr;
+    int clc_scratch_clusters = 0;
     int reeval_rs = 4;            // row slices per column-tile pair of its trailing update
     int update_ch = 8;
     // profiling
@@ -309,6 +314,56 @@ int launch_inverse_cl(kdsl_handle h, const int *list) {
     return KDSL_OK;
 }
 
+// ComplexF64 engine: both species in one launch of the complex cluster inverse (kdsl_inverse_cl_c.cuh) on the split planes
+// that k_gather_tilde_split_c left in A_up / A_dn; returns -1 when it does not apply.
+bool inverse_clc_applies(kdsl_handle h) {
+    if (!h->cplx || !(h->inverse_variant == 0 || h->inverse_variant == 9)) return false;
+    const int cl = h->inverse_cluster;
+    if (cl < 2 || cl > 8) return false;
+    const int NpMax = std::max(h->Npc_up, h->Npc_dn);
+    if (NpMax > 512 || std::min(h->Npc_up, h->Npc_dn) < 8) return false;
+    // the split planes live in the embedding's workspace: 2 Npc^2 <= Np^2 doubles per entry
+    if ((size_t)2 * h->Npc_up * h->Npc_up > (size_t)h->Np_up * h->Np_up || (size_t)2 * h->Npc_dn * h->Npc_dn > (size_t)h->Np_dn * h->Np_dn) return false;
+    return inverse_clc_smem(8, NpMax) <= (size_t)227 * 1024;
+}
+template <int NB, int CT, int T, int MINB>
+int launch_inverse_clc_t(kdsl_handle h, const int *list) {
+    const int NpMax = std::max(h->Npc_up, h->Npc_dn);
+    if (NpMax > T) return -1;                             // thread = matrix row in the pivot CTA
+    const int cl = h->inverse_cluster;
+    const size_t smem = inverse_clc_smem(NB, NpMax);
+    auto kern = k_inverse_cl_c<NB, CT, T, MINB>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cl * (MINB * h->num_sms / cl));
+    int ncl = 0;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) return -1;
+    ncl = std::min(ncl, MINB * h->num_sms / cl);
+    if (getenv("KDSL_DEBUG_OCC")) fprintf(stderr, "k_inverse_cl_c<%d,%d,%d,%d>: cluster size %d, %d active clusters, smem %zu\n", NB, CT, T, MINB, cl, ncl, smem);
+    if (!h->clc_scratch || h->clc_scratch_clusters < ncl) {
+        int rc = dev_alloc(h, &h->clc_scratch, (size_t)ncl * inverse_clc_scratch_doubles(16, NpMax));
+        if (rc) return rc;
+        h->clc_scratch_clusters = ncl;
+    }
+    cfg.gridDim = dim3(cl * ncl);
+    const int cs = std::max(h->Np_up, h->Np_dn), rs = std::max(1, h->inverse_rs);
+    const size_t su = (size_t)h->Np_up * h->Np_up, sd = (size_t)h->Np_dn * h->Np_dn;
+    CK(cudaLaunchKernelEx(&cfg, kern, h->S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Npc_up, h->Npc_dn, su, sd, cs, h->clc_scratch, rs));
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+int launch_inverse_clc(kdsl_handle h, const int *list) {
+    const int NpMax = std::max(h->Npc_up, h->Npc_dn);
+    const int v = h->inverse_tuning & 15;
+    if (NpMax <= 256 && v != 1) return launch_inverse_clc_t<8, 2, 256, 2>(h, list);   // two CTAs per SM: twice the matrices in flight
+    return launch_inverse_clc_t<8, 2, 512, 1>(h, list);
+}
+
 // reevaluateW! as ONE cluster kernel (kdsl_reeval_cl.cuh); returns -1 when it does not apply.
 int launch_reeval_cl(kdsl_handle h, const int *list) {
     if (!h->rcl_ok || h->cplx) return -1;
@@ -400,6 +455,39 @@ int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) 
 int launch_refresh(kdsl_handle h, const int *list) {
     const DevState &S = h->S;
     const int Nmax = std::max(S.n_up, S.n_dn);
+    if (inverse_clc_applies(h)) {
+        // ComplexF64: complex blocked Gauss-Jordan by clusters on split (re, im) planes, then W = U X on the unoccupied rows
+        const int cs = std::max(h->Np_up, h->Np_dn);
+        const size_t su = (size_t)h->Np_up * h->Np_up, sd = (size_t)h->Np_dn * h->Np_dn;
+        int rc;
+        {
+            Span sp(h, KDSL_T_REFRESH_GATHER);
+            k_gather_tilde_split_c<<<dim3(S.nw, 2), 256, Nmax * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->Npc_up, h->Npc_dn, su, sd);
+            CK(cudaGetLastError());
+        }
+        {
+            Span sp(h, KDSL_T_REFRESH_INVERSE);
+            rc = launch_inverse_clc(h, list);
+            if (rc > 0) return rc;
+            if (rc == 0) {
+                k_refresh_status<<<(S.nw + 255) / 256, 256, 0, h->stream>>>(S, list, h->status);
+                CK(cudaGetLastError());
+                h->t_launch[KDSL_T_REFRESH_INVERSE] += 1;
+            }
+        }
+        if (rc == 0) {
+            Span sp(h, KDSL_T_REFRESH_GEMM);
+            k_unsplit_c<<<dim3(S.nw, 2), 256, std::max(h->Npc_up, h->Npc_dn) * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Npc_up, h->Npc_dn, su, sd, cs, h->urow, S.ns);
+            CK(cudaGetLastError());
+            constexpr int BM = 64, BN = 32;
+            const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
+            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status, h->urow, S.ns);
+            CK(cudaGetLastError());
+            h->t_launch[KDSL_T_REFRESH_GEMM] += 1;
+            return KDSL_OK;
+        }
+        // (no cluster launch possible: fall through to the embedding, which rebuilds the workspace)
+    }
     if (h->cplx && h->inverse_variant != 1) {
         // ComplexF64: inverse of tilde_U through its real 2N x 2N embedding on the production real kernels
         if (std::max(h->Np_up, h->Np_dn) > 1024)
@@ -956,6 +1044,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
     if (cplx) {
         // the refresh workspace holds the real embedding [[X, -Y], [Y, X]] of tilde_U, padded: Np = roundup(2 N, 8)
         h->Np_up = (2 * n_up + 7) / 8 * 8; h->Np_dn = (2 * n_dn + 7) / 8 * 8;
+        h->Npc_up = (n_up + 7) / 8 * 8; h->Npc_dn = (n_dn + 7) / 8 * 8;
         ALLOC(h->A_up, nw * h->Np_up * h->Np_up); ALLOC(h->A_dn, nw * h->Np_dn * h->Np_dn);
         ALLOC(h->X_up, 2 * nw * n_up * n_up); ALLOC(h->X_dn, 2 * nw * n_dn * n_dn);
     } else {
@@ -1509,9 +1598,9 @@ int kdsl_reset_timers(kdsl_handle h) {
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (h && h->cplx && name) {
         const std::string nm(name);
-        if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5 && value != 7) ||
+        if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5 && value != 7 && value != 9) ||
             nm == "flush_variant")
-            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; inverse_variant 0/4/5/7 = real-embedding blocked inverse, 1 = unblocked complex)", name, (long long)value);
+            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; inverse_variant 0 / 9 = complex cluster inverse, 4 / 5 / 7 = blocked inverse of the real embedding, 1 = unblocked complex)", name, (long long)value);
         if (nm == "update_variant" && value == 2 && measure_wb_smem_c(h->S) > h->smem_optin)
             return fail(KDSL_ERR_INVALID_ARGUMENT, "the ComplexF64 Woodbury kernels need %zu bytes of shared memory at ns = %d (device limit %zu)",
                         measure_wb_smem_c(h->S), h->S.ns, h->smem_optin);
@@ -1554,7 +1643,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
 #ifndef KDSL_DEV_VARIANTS
         if (value == 2 || value == 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
 #endif
-        if (value < 0 || value > 8) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5, 6, 7 or 8");
+        if (value < 0 || value > 9 || (value == 9 && !h->cplx)) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5, 6, 7 or 8 (9: ComplexF64 engine only)");
         h->inverse_variant = (int)value;
     }
     else if (n == "fuse_sweeps") h->fuse_sweeps = (int)value;

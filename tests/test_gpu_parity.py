@@ -532,8 +532,8 @@ def test_full_size_invariants(kd, n, nw, n_sweeps):
 
 # ---- ComplexF64 mode: Peierls flux B != 0, complex Hermitian hopping matrix ----------------
 
-def _complex_problem(kd, n1, n2, B):
-    lat, ham = U.problem(n1, n2, (True, True), (True, False), "pi", None, B)
+def _complex_problem(kd, n1, n2, B, N_up=None):
+    lat, ham = U.problem(n1, n2, (True, True), (True, False), "pi", N_up, B)
     assert np.iscomplexobj(ham.U_up) and np.abs(np.asarray(ham.U_up).imag).max() > 1e-3
     return lat, ham
 
@@ -548,9 +548,10 @@ def test_complex_refresh_update_measure_match_oracle(kd, n1, n2, B):
     assert eng.is_complex
     eng.set_config(ku, kdn)
     orc = U.oracle_walkers(ham, ku, kdn, dtype="c128")
-    # inverse_variant 0 (default): inverse through the real 2N x 2N embedding on the blocked DMMA kernels;
+    # inverse_variant 0 (default) / 9: complex blocked Gauss-Jordan by thread-block clusters on split (re, im) planes;
+    # 5 / 7: inverse through the real 2N x 2N embedding on the blocked DMMA kernels (one CTA / one cluster per matrix);
     # 1: the reference-style unblocked complex Gauss-Jordan
-    for variant in (1, 5, 7, 0):
+    for variant in (1, 5, 7, 9, 0):
         eng.set_option("inverse_variant", variant)
         eng.set_W(0, 0, np.zeros_like(np.asarray(orc[0].W()[0])))           # make sure the refresh really rewrites W
         eng.refresh()
@@ -576,6 +577,57 @@ def test_complex_refresh_update_measure_match_oracle(kd, n1, n2, B):
         assert U.relerr(eng.get_W(w, 1), Wd2) < TOL
     with pytest.raises(kd.KdslError):
         eng.set_option("flush_variant", 3)                                  # the bulk-async flush is real-only
+    eng.close()
+
+
+@pytest.mark.parametrize("n,N_up,B,cluster,row_slices,nw", [
+    (6, None, 0.11, 4, 8, 80), (6, 50, 0.11, 2, 1, 20), (8, 97, 0.05, 4, 8, 40), (8, None, 0.05, 5, 3, 40), (8, None, 0.05, 8, 2, 20)])
+def test_complex_cluster_inverse_matches_oracle(kd, n, N_up, B, cluster, row_slices, nw):
+    """k_inverse_cl_c (ComplexF64 engine: complex blocked Gauss-Jordan, one matrix per thread-block cluster, split re / im
+    planes, four real DMMAs per complex block product): N not a multiple of 8, N_up != N_down (scripts/LL.jl filling),
+    more (walker, species) items than resident clusters, all cluster sizes' work splits, scratch reuse"""
+    lat, ham = _complex_problem(kd, n, n, B, N_up=N_up)
+    ns = kd.ns(lat)
+    rng = np.random.default_rng(500 + n + cluster)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
+    eng = kd.Engine(ham, nw)
+    assert eng.is_complex
+    eng.set_option("inverse_variant", 9)
+    eng.set_option("inverse_cluster", cluster)
+    eng.set_option("inverse_row_slices", row_slices)
+    eng.set_config(ku, kdn)
+    for rep in range(2):
+        eng.set_W(0, 0, np.zeros((ns, ham.N_up), dtype=np.complex128))
+        eng.refresh()
+    for w, mc in enumerate(U.oracle_walkers(ham, ku, kdn, dtype="c128")):
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL
+        assert U.relerr(eng.get_W(w, 1), Wd) < TOL
+    assert eng.accumulators()[kd._lib.ACC_N_SINGULAR] == 0
+    eng.close()
+
+
+def test_complex_cluster_inverse_singular_matrix_is_flagged(kd):
+    lat, ham = _complex_problem(kd, 6, 6, 0.11)
+    ns, nw = kd.ns(lat), 45
+    rng = np.random.default_rng(78)
+    ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
+    Ud = np.array(ham.U_down, dtype=np.complex128).copy()
+    bad_sites = np.nonzero(kdn[7])[0]
+    Ud[bad_sites[0], :] = 0.0
+    ham2 = kd.Hamiltonian(ham.N_up, ham.N_down, ham.U_up, Ud, ham.H_mat, ham.nn)
+    expect_bad = np.array([kdn[w, bad_sites[0]] != 0 for w in range(nw)])
+    assert expect_bad[7] and not expect_bad.all()
+    eng = kd.Engine(ham2, nw)
+    assert eng.is_complex
+    eng.set_config(ku, kdn)
+    with pytest.raises(kd.SingularException):
+        eng.refresh()
+    fl = eng.flags()
+    assert np.array_equal((fl & 1) != 0, expect_bad)
+    for w in np.nonzero(~expect_bad)[0][:6]:
+        Wd_ref = Ud @ np.linalg.inv(kd.tilde_U(Ud, kdn[w]))
+        assert U.relerr(eng.get_W(int(w), 1), Wd_ref) < 1e-8
     eng.close()
 
 

@@ -1,0 +1,27 @@
+#!/bin/bash
+# round-2 session 3: complex cluster inverse k_inverse_cl_c bring-up (parity first, then 432-site c128 timing)
+mkdir -p gpurun_out
+export KDSL_DEBUG_OCC=1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_headline.py -m gpu -x -q -k "complex or c128" > gpurun_out/r3d_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r3d_pytest.log
+tail -25 gpurun_out/r3d_pytest.log
+run() {
+  tag=$1; shift
+  timeout 300 python tools/quick_bench.py --n 12 --B 0.02 --walkers 4096 --sweeps 216 --therm 216 "$@" > gpurun_out/r3d_qc128_$tag.log 2>&1
+  echo "== c128 432 $tag"; grep -E "walker_sweeps_per_s|k_inverse_cl_c" gpurun_out/r3d_qc128_$tag.log | head -2
+  python - gpurun_out/r3d_qc128_$tag.log <<'PY'
+import sys,re,json
+t=open(sys.argv[1]).read()
+i=t.find('{'); j=t.rfind('}')
+try:
+    d=json.loads(t[i:j+1]); print({k:(round(v["ms"],2),v["launches"]) for k,v in d["timers"].items()}, d["E_site"], d["n_singular"])
+except Exception as e: print("ERR",e, t[-800:])
+PY
+}
+run v7 --opt inverse_variant=7
+run v0_cl4
+run v0_cl3 --opt inverse_cluster=3
+run v0_cl2 --opt inverse_cluster=2
+run v0_cl5 --opt inverse_cluster=5
+run v0_cl4_rs4 --opt inverse_row_slices=4
+run v0_cl4_rs2 --opt inverse_row_slices=2
+run v0_cl4_rs16 --opt inverse_row_slices=16
