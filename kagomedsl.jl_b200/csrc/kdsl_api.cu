@@ -132,6 +132,7 @@ struct kdsl_handle_s {
     int Npc_up = 0, Npc_dn = 0;   // complex tilde_U dimensions padded to a multiple of 8
     double *clc_scratch = nullptr;
     int clc_scratch_clusters = 0;
+    int fdc_RB = 0;               // rows per item of k_flush_dmma_c (0: it does not fit, k_flush_c runs)
     int reeval_rs = 4;            // row slices per column-tile pair of its trailing update
     int update_ch = 8;
     // profiling
@@ -314,6 +315,22 @@ int launch_inverse_cl(kdsl_handle h, const int *list) {
     return KDSL_OK;
 }
 
+// ComplexF64 engine: W = U X on the unoccupied rows (FP64 FMA tiles; gemm_variant picks the tile shape)
+int launch_gemm_W_c(kdsl_handle h, const int *list) {
+    const DevState &S = h->S;
+    const int Nmax = std::max(S.n_up, S.n_dn);
+#define KDSL_GEMM_C(BM, BN, BK)                                                                                     \
+    do {                                                                                                            \
+        const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);                                          \
+        k_gemm_W_c<BM, BN, BK><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status, h->urow, S.ns); \
+    } while (0)
+    if (h->gemm_variant == 4) KDSL_GEMM_C(64, 64, 8);
+    else KDSL_GEMM_C(64, 32, 8);                          // (64 x 64 and deeper k tiles measured 5 % slower, 128 x 64 50 % slower)
+#undef KDSL_GEMM_C
+    CK(cudaGetLastError());
+    return KDSL_OK;
+}
+
 // ComplexF64 engine: both species in one launch of the complex cluster inverse (kdsl_inverse_cl_c.cuh) on the split planes
 // that k_gather_tilde_split_c left in A_up / A_dn; returns -1 when it does not apply.
 bool inverse_clc_applies(kdsl_handle h) {
@@ -324,7 +341,7 @@ bool inverse_clc_applies(kdsl_handle h) {
     if (NpMax > 512 || std::min(h->Npc_up, h->Npc_dn) < 8) return false;
     // the split planes live in the embedding's workspace: 2 Npc^2 <= Np^2 doubles per entry
     if ((size_t)2 * h->Npc_up * h->Npc_up > (size_t)h->Np_up * h->Np_up || (size_t)2 * h->Npc_dn * h->Npc_dn > (size_t)h->Np_dn * h->Np_dn) return false;
-    return inverse_clc_smem(8, NpMax) <= (size_t)227 * 1024;
+    return inverse_clc_smem(16, NpMax) <= (size_t)227 * 1024;
 }
 template <int NB, int CT, int T, int MINB>
 int launch_inverse_clc_t(kdsl_handle h, const int *list) {
@@ -360,7 +377,12 @@ int launch_inverse_clc_t(kdsl_handle h, const int *list) {
 int launch_inverse_clc(kdsl_handle h, const int *list) {
     const int NpMax = std::max(h->Npc_up, h->Npc_dn);
     const int v = h->inverse_tuning & 15;
-    if (NpMax <= 256 && v != 1) return launch_inverse_clc_t<8, 2, 256, 2>(h, list);   // two CTAs per SM: twice the matrices in flight
+    // two CTAs per SM double the matrices in flight (26.6 ms against 35.1 per 4096-walker bin at 432 sites); panels of 16
+    // complex columns halve the block steps (21.8 ms)
+    // (measured slower: three 224-thread CTAs per SM with panels of 8: 31.8 ms, 224-thread CTAs with panels of 16: 23.9 ms)
+    if (NpMax <= 256 && v == 2) return launch_inverse_clc_t<8, 2, 256, 2>(h, list);
+    if (NpMax <= 256 && v != 1 && 2 * (inverse_clc_smem(16, NpMax) + 1024) <= (size_t)227 * 1024) return launch_inverse_clc_t<16, 2, 256, 2>(h, list);
+    if (NpMax <= 256 && v != 1) return launch_inverse_clc_t<8, 2, 256, 2>(h, list);
     return launch_inverse_clc_t<8, 2, 512, 1>(h, list);
 }
 
@@ -477,12 +499,18 @@ int launch_refresh(kdsl_handle h, const int *list) {
         }
         if (rc == 0) {
             Span sp(h, KDSL_T_REFRESH_GEMM);
-            k_unsplit_c<<<dim3(S.nw, 2), 256, std::max(h->Npc_up, h->Npc_dn) * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Npc_up, h->Npc_dn, su, sd, cs, h->urow, S.ns);
+            const bool dm = h->gemm_variant != 4 && Nmax <= 512;      // tensor-pipe product straight from the split planes
+            k_unsplit_c<<<dim3(S.nw, 2), 256, std::max(h->Npc_up, h->Npc_dn) * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Npc_up, h->Npc_dn, su, sd, cs, h->urow, S.ns, dm ? 0 : 1);
             CK(cudaGetLastError());
-            constexpr int BM = 64, BN = 32;
-            const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
-            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status, h->urow, S.ns);
-            CK(cudaGetLastError());
+            if (dm) {
+                const int Mmax = S.ns - std::min(S.n_up, S.n_dn);
+                const int tiles = ((Mmax + 71) / 72) * ((Nmax + 23) / 24);
+                k_gemm_W_dmma_c<8><<<dim3(tiles, S.nw, 2), 96, 0, h->stream>>>(S, list, h->A_up, h->A_dn, h->status, h->colsrc, h->Npc_up, h->Npc_dn, su, sd, cs, h->urow, S.ns);
+                CK(cudaGetLastError());
+            } else {
+                int rg = launch_gemm_W_c(h, list);
+                if (rg) return rg;
+            }
             h->t_launch[KDSL_T_REFRESH_GEMM] += 1;
             return KDSL_OK;
         }
@@ -515,10 +543,8 @@ int launch_refresh(kdsl_handle h, const int *list) {
             Span sp(h, KDSL_T_REFRESH_GEMM);
             k_unembed_c<<<dim3(S.nw, 2), 256, cs * sizeof(int), h->stream>>>(S, list, h->A_up, h->A_dn, h->X_up, h->X_dn, h->status, h->colsrc, h->Np_up, h->Np_dn, cs, h->urow, S.ns);
             CK(cudaGetLastError());
-            constexpr int BM = 64, BN = 32;
-            const int tiles = ((S.ns + BM - 1) / BM) * ((Nmax + BN - 1) / BN);
-            k_gemm_W_c<BM, BN, 8><<<dim3(tiles, S.nw, 2), 256, 0, h->stream>>>(S, list, h->X_up, h->X_dn, h->status, h->urow, S.ns);
-            CK(cudaGetLastError());
+            int rg = launch_gemm_W_c(h, list);
+            if (rg) return rg;
             h->t_launch[KDSL_T_REFRESH_GEMM] += 1;
         }
         return KDSL_OK;
@@ -692,7 +718,12 @@ int launch_flush(kdsl_handle h, bool all) {
         const int per_sm = 2 * (smem + 12 * 1024) <= (size_t)227 * 1024 ? 2 : 1;
         {
             Span sp(h, KDSL_T_UPDATE);
-            k_flush_c<24, 216><<<h->num_sms * per_sm, 224, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Np);
+            if (h->flush_variant == 0 && h->fdc_RB > 0) {     // tensor-pipe flush (k_flush_dmma_c), one persistent CTA per SM
+                const int Npad = (Np + 7) / 8 * 8;
+                k_flush_dmma_c<24, 3><<<h->num_sms, 512, flush_dmma_c_smem(24, Npad, h->fdc_RB), h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Npad, h->fdc_RB);
+            } else {
+                k_flush_c<24, 216><<<h->num_sms * per_sm, 224, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Np);
+            }
             CK(cudaGetLastError());
         }
         k_flush_finish_wb<<<1, 1024, 0, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5);
@@ -1133,6 +1164,17 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
         CKD(cudaFuncGetAttributes(&fa, (const void *)k_flush_c<24, 216>));
         CKD(cudaFuncSetAttribute(k_flush_c<24, 216>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        {
+            // k_flush_dmma_c: the fewest row blocks per species whose operands fit the shared memory
+            CKD(cudaFuncGetAttributes(&fa, (const void *)k_flush_dmma_c<24, 3>));
+            const size_t lim = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+            const int Npad = (std::max(n_up, n_dn) + 7) / 8 * 8;
+            for (int nrb = 1; nrb <= 64 && !h->fdc_RB; nrb++) {
+                const int RB = (((int)ns + nrb - 1) / nrb + 7) / 8 * 8;
+                if (flush_dmma_c_smem(24, Npad, RB) <= lim) h->fdc_RB = RB;
+            }
+            if (h->fdc_RB) CKD(cudaFuncSetAttribute(k_flush_dmma_c<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_dmma_c_smem(24, Npad, h->fdc_RB)));
+        }
         const size_t need_f = (size_t)24 * std::max(n_up, n_dn) * 2 * sizeof(double);
         if (measure_wb_smem_c(S) > h->smem_optin || need_f + fa.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) {
             // too large for the Woodbury kernels' shared memory: the reference's immediate rank-1 update (any size)
@@ -1599,8 +1641,8 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (h && h->cplx && name) {
         const std::string nm(name);
         if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5 && value != 7 && value != 9) ||
-            nm == "flush_variant")
-            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; inverse_variant 0 / 9 = complex cluster inverse, 4 / 5 / 7 = blocked inverse of the real embedding, 1 = unblocked complex)", name, (long long)value);
+            (nm == "flush_variant" && value != 0 && value != 4))
+            return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; flush_variant 0 = tensor-pipe flush, 4 = FMA flush; inverse_variant 0 / 9 = complex cluster inverse, 4 / 5 / 7 = blocked inverse of the real embedding, 1 = unblocked complex)", name, (long long)value);
         if (nm == "update_variant" && value == 2 && measure_wb_smem_c(h->S) > h->smem_optin)
             return fail(KDSL_ERR_INVALID_ARGUMENT, "the ComplexF64 Woodbury kernels need %zu bytes of shared memory at ns = %d (device limit %zu)",
                         measure_wb_smem_c(h->S), h->S.ns, h->smem_optin);
@@ -1654,7 +1696,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
             if (rc) return rc;
             if ((rc = dev_alloc(h, &h->Gbuf, (size_t)2 * h->S.nw * h->Gstride))) return rc;
         }
-        if (value != 0 && value != 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+        if (value != 0 && value != 3 && !(h->cplx && value == 4)) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
 #endif
         h->flush_variant = (int)value;
     }

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256)
 k_unsplit_c(DevState S, const int *__restrict__ list, const double *__restrict__ A_up, const double *__restrict__ A_dn,
             double *__restrict__ X_up, double *__restrict__ X_dn, const int *__restrict__ status,
             const int *__restrict__ colsrc_base, int Np_up, int Np_dn, size_t str_up, size_t str_dn, int cs_stride,
-            int *__restrict__ urow_base, int urow_stride) {
+            int *__restrict__ urow_base, int urow_stride, int write_X) {
     extern __shared__ int s_row_of_step_sp[];
     const int b = blockIdx.x, spin = blockIdx.y;
     if (b >= batch_count(S, list)) return;
@@ -385,7 +385,7 @@ k_unsplit_c(DevState S, const int *__restrict__ list, const double *__restrict__
     const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
     for (int i = threadIdx.x; i < Np; i += blockDim.x) s_row_of_step_sp[colsrc[i]] = i;
     __syncthreads();
-    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    for (int e = threadIdx.x; e < (write_X ? N * N : 0); e += blockDim.x) {   // (k_gemm_W_dmma_c reads the planes itself)
         const int j = e / N, k = e - j * N;
         const size_t o = (size_t)colsrc[j] * Np + s_row_of_step_sp[k];
         X[e] = c_make(Ar[o], Ai[o]);
@@ -421,5 +421,135 @@ k_unsplit_c(DevState S, const int *__restrict__ list, const double *__restrict__
         const int l = kap[site];
         if (l != 0)
             for (int n = 0; n < N; n++) W[(size_t)n * ns + site] = c_make(l - 1 == n ? 1.0 : 0.0, 0.0);
+    }
+}
+
+// W[w][unoccupied sites, :] = U[unoccupied sites, :] * inv(tilde_U), complex, on the FP64 tensor pipe, straight from the split
+// planes k_inverse_cl_c left behind: with rho the stored row index, W[m, j] = sum_rho U[m, colsrc[rho]] S[rho, colsrc[j]]
+// (both permutations of the implicit pivoting folded into the operand loads; rows rho >= N are the identity padding).
+// A complex block product is four real DMMAs (the minus sign rides on a negated copy of the Im(U) fragment).
+// CTA = 3 warps, tile 72 sites x 24 columns (warp tile 24 x 24), four CTAs per SM (12 warps = 3 per sub-partition: a 9-warp
+// CTA loses 10-25 % to the 4-way split); register-staged double buffering, fragment-major shared layout.
+// grid (tiles_m * tiles_n, nw, 2).  The unit rows of the occupied sites and the urow lists come from k_unsplit_c.
+template <int KT>
+__global__ void __launch_bounds__(96, 4)
+k_gemm_W_dmma_c(DevState S, const int *__restrict__ list, const double *__restrict__ A_up, const double *__restrict__ A_dn,
+                const int *__restrict__ status, const int *__restrict__ colsrc_base, int Np_up, int Np_dn, size_t str_up,
+                size_t str_dn, int cs_stride, const int *__restrict__ urow_base, int urow_stride) {
+    constexpr int TM = 72, TN = 24, NT = 96, KS = KT / 4;
+    constexpr int PA = TM * KT / NT, PB = TN * KT / NT;
+    static_assert(TM * KT % NT == 0 && TN * KT % NT == 0 && KT % 4 == 0, "stage must divide evenly");
+    __shared__ double sAr[2][TM * KT], sAi[2][TM * KT], sBr[2][TN * KT], sBi[2][TN * KT];
+    __shared__ int sSrc[TN];
+    __shared__ int sRowSite[TM];
+    __shared__ int sKp[512 + KT];
+    const int b = blockIdx.y, spin = blockIdx.z;
+    if (b >= batch_count(S, list)) return;
+    if (status[2 * b] | status[2 * b + 1]) return;
+    const int w = list ? list[b] : b;
+    const int ns = S.ns, N = spin ? S.n_dn : S.n_up, Np = spin ? Np_dn : Np_up;
+    const int M = ns - N;
+    const int tiles_m = (M + TM - 1) / TM;
+    const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+    const int m0 = tm * TM, n0 = tn * TN;
+    if (n0 >= N) return;
+    const cplx *U = cW(spin ? S.U_dn : S.U_up, 0);
+    const double *Sr = (spin ? A_dn : A_up) + (size_t)b * (spin ? str_dn : str_up);
+    const double *Si = Sr + (size_t)Np * Np;
+    const int *colsrc = colsrc_base + ((size_t)2 * b + spin) * cs_stride;
+    const int *urow = urow_base + ((size_t)2 * b + spin) * urow_stride;
+    cplx *W = cW(spin ? S.W_dn : S.W_up, (size_t)w * ns * N);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
+    if (tid < TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
+    for (int k = tid; k < 512 + KT; k += NT) sKp[k] = k < N ? colsrc[k] : 0;
+    __syncthreads();
+
+    cplx ra[PA];
+    double rbr[PB], rbi[PB];
+    auto load_stage = [&](int kk) {
+#pragma unroll
+        for (int q = 0; q < PA; q++) {
+            const int e = tid + q * NT;
+            const int r = e % TM, k = e / TM;                      // A: gathered rows of U, permuted columns
+            const int site = sRowSite[r];
+            ra[q] = (site >= 0 && kk + k < N) ? U[(size_t)sKp[kk + k] * ns + site] : c_make(0.0, 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < PB; q++) {
+            const int e = tid + q * NT;
+            const int kb = e % KT, n = e / KT;                     // B: contiguous along the stored row index
+            const int src = sSrc[n];
+            const bool ok = src >= 0 && kk + kb < N;
+            rbr[q] = ok ? Sr[(size_t)src * Np + kk + kb] : 0.0;
+            rbi[q] = ok ? Si[(size_t)src * Np + kk + kb] : 0.0;
+        }
+    };
+    auto store_stage = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < PA; q++) {
+            const int e = tid + q * NT;
+            const int fi = frag_idx(e % TM, e / TM, KT);
+            sAr[buf][fi] = ra[q].x;
+            sAi[buf][fi] = ra[q].y;
+        }
+#pragma unroll
+        for (int q = 0; q < PB; q++) {
+            const int e = tid + q * NT;
+            const int fi = frag_idx(e / KT, e % KT, KT);
+            sBr[buf][fi] = rbr[q];
+            sBi[buf][fi] = rbi[q];
+        }
+    };
+    double cr[3][3][2], ci[3][3][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+    load_stage(0);
+    store_stage(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kk = 0; kk < N; kk += KT) {
+        const bool more = kk + KT < N;
+        if (more) load_stage(kk + KT);
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            double ar[3], ai[3], an[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                ar[i] = sAr[buf][((((warp * 3 + i) * KS) + s) << 5) + lane];
+                ai[i] = sAi[buf][((((warp * 3 + i) * KS) + s) << 5) + lane];
+                an[i] = -ai[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double br = sBr[buf][(((j * KS) + s) << 5) + lane], bi = sBi[buf][(((j * KS) + s) << 5) + lane];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    dmma_8x8x4(cr[i][j][0], cr[i][j][1], ar[i], br);
+                    dmma_8x8x4(ci[i][j][0], ci[i][j][1], ar[i], bi);
+                    dmma_8x8x4(cr[i][j][0], cr[i][j][1], an[i], bi);
+                    dmma_8x8x4(ci[i][j][0], ci[i][j][1], ai[i], br);
+                }
+            }
+        }
+        if (more) store_stage(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+    const int gr = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int n = n0 + 8 * j + 2 * tg + e;
+            if (n >= N) continue;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int site = sRowSite[24 * warp + 8 * i + gr];
+                if (site >= 0) W[(size_t)n * ns + site] = c_make(cr[i][j][e], ci[i][j][e]);
+            }
+        }
     }
 }

@@ -14,6 +14,7 @@
 #include "kdsl_common.cuh"
 #include "kdsl_complex.cuh"
 #include "kdsl_woodbury.cuh"
+#include "kdsl_refresh_fast.cuh"
 
 struct WbViewC {
     const cplx *W0;
@@ -345,6 +346,151 @@ k_flush_c(DevState S, const int *__restrict__ list, const int *__restrict__ coun
                 if (j0 + q < N) W0[(size_t)(j0 + q) * ns + row] = a[q];
         }
     }
+}
+
+// k_flush_dmma_c: the same pass W0 += C G on the FP64 TENSOR pipe.  k_flush_c is bound by its shared-memory broadcasts (one
+// LDS.128 per complex FMA); here a complex block product is four real DMMAs on split (re, im) operand planes in DMMA
+// fragment order,  Dr += Gr Cr - Gi Ci,  Di += Gr Ci + Gi Cr,  in the transposed form of k_flush_wb: the accumulator fragment
+// of a lane is (column j, rows 2t, 2t + 1) = 32 contiguous bytes of the interleaved column-major W0, so every lane moves
+// two 128-bit words per tile and direction.  Item = (list entry, species, block of RB rows) pulled from a device counter by
+// persistent CTAs (one per SM, 16 warps); per item: T and the displaced labels -> G = -T Rt for all columns (FMA, all
+// threads) and the rows' entries of C = W0[:, (l_m)] -> shared memory; then warp w streams the column tiles w, w + 16, ...
+// over the block's row tiles with its G fragments in registers, D tiles of loads in flight behind the DMMAs.
+// Dynamic smem: G planes 2 [Npad x KP] + C planes 2 [RB x KP] doubles + T [KP x KP] complex + labels.
+template <int KP, int D>
+__global__ void __launch_bounds__(512, 1)
+k_flush_dmma_c(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
+               int *__restrict__ work_counter, int Npad, int RB) {
+    constexpr int KS = KP / 4, T_ = 512, NWARPS = 16;
+    extern __shared__ __align__(16) unsigned char fdsm[];
+    double *sGr = reinterpret_cast<double *>(fdsm);       // [Npad x KP] frag-major (r = column j, k = m): Re G[m][j]
+    double *sGi = sGr + (size_t)Npad * KP;
+    double *sCr = sGi + (size_t)Npad * KP;                // [RB x KP] frag-major (r = row, k = m): Re W0[row, l_m]
+    double *sCi = sCr + (size_t)RB * KP;
+    cplx *sT = reinterpret_cast<cplx *>(sCi + (size_t)RB * KP);   // [cnt x cnt] packed
+    int *sL = reinterpret_cast<int *>(sT + KP * KP);
+    __shared__ int s_item;
+    const int count = count_ptr ? *count_ptr : count_fixed;
+    const int ns = S.ns;
+    const int nrb = (ns + RB - 1) / RB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gr = lane >> 2, tg = lane & 3;
+    const int total = count * 2 * nrb;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int e = item / (2 * nrb);
+        const int rem = item - e * 2 * nrb;
+        const int spin = rem / nrb, rb = rem - spin * nrb;
+        const int w = list ? list[e] : e;
+        const WbViewC v = wb_view_c(S, w, spin);
+        const int cnt = v.k;
+        if (cnt == 0) continue;                           // uniform over the block
+        const int N = v.N;
+        const int nks = (cnt + 3) >> 2;                   // k-steps that hold pending updates
+        double *W0 = reinterpret_cast<double *>(const_cast<cplx *>(v.W0));
+        for (int x = tid; x < cnt * cnt; x += T_) sT[x] = v.T[(x / cnt) * S.kmax + (x % cnt)];
+        if (tid < KP) sL[tid] = tid < cnt ? v.Ls[tid] : -1;
+        __syncthreads();
+        // G[m][j] = -sum_n T[m][n] (W0[K_n, j] - delta(l_n, j)); zero for m >= cnt and for the padding columns.
+        // A thread owns column j and half of the m range: every row copy is read once per half.
+        for (int idx = tid; idx < 2 * Npad; idx += T_) {
+            constexpr int MG = KP / 2;
+            const int mg = idx / Npad, j = idx - mg * Npad;
+            cplx acc[MG];
+#pragma unroll
+            for (int q = 0; q < MG; q++) acc[q] = c_make(0.0, 0.0);
+            if (j < N && mg * MG < cnt) {
+                for (int n = 0; n < cnt; n++) {
+                    cplx rt = v.rows[(size_t)n * N + j];
+                    if (sL[n] == j) rt.x -= 1.0;
+#pragma unroll
+                    for (int q = 0; q < MG; q++)
+                        if (mg * MG + q < cnt) acc[q] = c_fma(sT[(mg * MG + q) * cnt + n], rt, acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < MG; q++) {
+                const int m = mg * MG + q;
+                if (m < 4 * nks) {
+                    const int fi = frag_idx(j, m, KP);
+                    sGr[fi] = -acc[q].x;
+                    sGi[fi] = -acc[q].y;
+                }
+            }
+        }
+        // C[row][m] = W0[row, l_m] for the rows of this block (all of them read before any store of this item)
+        const int r0 = rb * RB, nrows = min(RB, ns - r0);
+        const int nrt = (nrows + 7) >> 3;
+        for (int idx = tid; idx < (nrt << 3) * (4 * nks); idx += T_) {
+            const int m = idx / (nrt << 3), r = idx - m * (nrt << 3);
+            cplx c = c_make(0.0, 0.0);
+            if (m < cnt && r < nrows) c = v.W0[(size_t)sL[m] * ns + r0 + r];
+            const int fi = frag_idx(r, m, KP);
+            sCr[fi] = c.x;
+            sCi[fi] = c.y;
+        }
+        __syncthreads();
+        const int njt = (N + 7) >> 3;
+        for (int jt = warp; jt < njt; jt += NWARPS) {
+            double g_r[KS], g_i[KS], g_n[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                g_r[ks] = ks < nks ? sGr[(((jt * KS) + ks) << 5) + lane] : 0.0;
+                g_i[ks] = ks < nks ? sGi[(((jt * KS) + ks) << 5) + lane] : 0.0;
+                g_n[ks] = -g_i[ks];
+            }
+            const int j = (jt << 3) + gr;
+            const bool jok = j < N;
+            // lane's 32 bytes of a tile: rows r0 + rt*8 + 2 tg, + 1 of column j (interleaved re, im)
+            double *base = W0 + 2 * ((size_t)j * ns + r0 + 2 * tg);
+            double2 b0[D], b1[D];
+            auto ld = [&](int rt, double2 &x0, double2 &x1) {
+                const int rl = min(rt, nrt - 1);
+                const int row = (rl << 3) + 2 * tg;
+                const double2 *p = reinterpret_cast<const double2 *>(base + 16 * rl);
+                x0 = (jok && row < nrows) ? __ldcs(p) : make_double2(0.0, 0.0);
+                x1 = (jok && row + 1 < nrows) ? __ldcs(p + 1) : make_double2(0.0, 0.0);
+            };
+            auto tile = [&](int rt, double2 &x0, double2 &x1) {
+                double2 cr = make_double2(x0.x, x1.x), ci = make_double2(x0.y, x1.y);
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    if (ks < nks) {
+                        const double br = sCr[(((rt * KS) + ks) << 5) + lane], bi = sCi[(((rt * KS) + ks) << 5) + lane];
+                        dmma_8x8x4(cr.x, cr.y, g_r[ks], br);
+                        dmma_8x8x4(ci.x, ci.y, g_r[ks], bi);
+                        dmma_8x8x4(cr.x, cr.y, g_n[ks], bi);
+                        dmma_8x8x4(ci.x, ci.y, g_i[ks], br);
+                    }
+                }
+                const int row = (rt << 3) + 2 * tg;
+                double2 *p = reinterpret_cast<double2 *>(base + 16 * rt);
+                if (jok && row < nrows) __stcs(p, make_double2(cr.x, ci.x));
+                if (jok && row + 1 < nrows) __stcs(p + 1, make_double2(cr.y, ci.y));
+            };
+#pragma unroll
+            for (int i = 0; i < D; i++) ld(i, b0[i], b1[i]);
+            int rt0 = 0;
+#pragma unroll 1
+            for (; rt0 + D <= nrt; rt0 += D) {
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    tile(rt0 + i, b0[i], b1[i]);
+                    ld(rt0 + i + D, b0[i], b1[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D - 1; i++)
+                if (rt0 + i < nrt) tile(rt0 + i, b0[i], b1[i]);
+        }
+    }
+}
+inline size_t flush_dmma_c_smem(int KP, int Npad, int RB) {
+    return ((size_t)2 * Npad * KP + (size_t)2 * RB * KP + (size_t)2 * KP * KP) * sizeof(double) + (size_t)KP * sizeof(int);
 }
 
 // O_L (getOL, src/Hamiltonian.jl:762-778) with complex Woodbury-form W; one CTA (256 threads) per walker

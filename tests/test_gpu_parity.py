@@ -631,11 +631,11 @@ def test_complex_cluster_inverse_singular_matrix_is_flagged(kd):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [2, 0])
-def test_complex_replay_and_device_rng_match_oracle(kd, variant):
+@pytest.mark.parametrize("variant,flush", [(2, 0), (2, 4), (0, 0)])
+def test_complex_replay_and_device_rng_match_oracle(kd, variant, flush):
     """ComplexF64 chain: replayed proposals -> kappa / Z_mu / counters bit-exact, W within 1e-10; device Xoshiro ->
-    same trajectory, counters and O_L sums as the oracle's Carlo loop.  variant 2 = Woodbury delayed updates (default),
-    0 = the reference's immediate rank-1 update."""
+    same trajectory, counters and O_L sums as the oracle's Carlo loop.  variant 2 = Woodbury delayed updates (default;
+    flush 0 = tensor-pipe flush k_flush_dmma_c, 4 = FMA flush k_flush_c), 0 = the reference's immediate rank-1 update."""
     lat, ham = _complex_problem(kd, 4, 3, 0.37)
     ns, nw, n_sweeps = kd.ns(lat), 6, 900
     rng = np.random.default_rng(8)
@@ -645,6 +645,7 @@ def test_complex_replay_and_device_rng_match_oracle(kd, variant):
     bond = rng.integers(1, len(ham.nn) + 1, size=(n_sweeps, nw)).astype(np.int32)
     eng = kd.Engine(ham, nw)
     eng.set_option("update_variant", variant)
+    eng.set_option("flush_variant", flush)
     eng.set_config(ku, kdn)
     eng.refresh()
     eng.replay(r, bond)
@@ -670,6 +671,7 @@ def test_complex_replay_and_device_rng_match_oracle(kd, variant):
     states = kd.walker_states(3, nw)
     eng = kd.Engine(ham, nw)
     eng.set_option("update_variant", variant)
+    eng.set_option("flush_variant", flush)
     eng.set_config(ku, kdn)
     eng.set_rng(states)
     eng.refresh()
