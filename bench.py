@@ -360,7 +360,7 @@ def run_ours(args):
     # per ACCEPTED move.
     if woodbury:
         n_units, unit_name = upd["flushes"], "walker flush"
-        kname = ("k_flush_c (delayed rank-k update of the ComplexF64 W, FP64 FMA, one thread per row)" if cplx else
+        kname = ("k_flush_dmma_c (delayed rank-k update of the ComplexF64 W: four real DMMAs per complex block product, 128-bit streaming)" if cplx else
                  "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)")
         n_launch = max(upd["launches"] // 2, 1)
     else:
@@ -418,13 +418,17 @@ def run_ours(args):
             "k_reeval_fused_dram_bytes_per_walker_refresh", flop_survey)
         cands.append(roofline_inverse)
     elif tm["refresh_inverse"]["launches"] > 0:
-        Ne = 2 * Nh if cplx else Nh                      # ComplexF64: inverse through the real 2N x 2N embedding
-        roofline_inverse = tensor_roofline("k_inverse_v5 / k_inverse_v4 (batched blocked Gauss-Jordan inverse of tilde_U, FP64 DMMA trailing update)",
-                                           2.0 * 2.0 * Ne ** 3, tm["refresh_inverse"]["ms"], 2 * K, "k_inverse_v4_dram_bytes_per_matrix",
+        # ComplexF64: complex elimination on split (re, im) planes (k_inverse_cl_c): N^3 complex multiply-adds per matrix
+        iname = ("k_inverse_cl_c (ComplexF64: blocked Gauss-Jordan inverse of tilde_U, one matrix per thread-block cluster, four real DMMAs per complex block product)"
+                 if cplx else
+                 "k_inverse_cl / k_inverse_v5 / k_inverse_v4 (batched blocked Gauss-Jordan inverse of tilde_U, FP64 DMMA trailing update; one cluster per matrix for N > 256)")
+        roofline_inverse = tensor_roofline(iname, cmul * 2.0 * 2.0 * Nh ** 3, tm["refresh_inverse"]["ms"], 2 * K,
+                                           "k_inverse_cl_c_dram_bytes_per_walker_refresh" if cplx else "k_inverse_v4_dram_bytes_per_matrix",
                                            cmul * 2.0 * 2.0 * Nh ** 3)
         # (the rows of W on occupied sites are unit vectors and are written, not computed: the kernel executes
         #  2 (ns - N) N^2 flops per matrix where the reference's full product has 2 ns N^2)
-        roofline_gemm = tensor_roofline("k_gemm_W_dmma / k_gemm_W_c (W = U inv(tilde_U) on the unoccupied rows)",
+        roofline_gemm = tensor_roofline("k_gemm_W_dmma_c (ComplexF64: W = U inv(tilde_U) on the unoccupied rows, straight from the split planes)" if cplx
+                                        else "k_gemm_W_dmma (W = U inv(tilde_U) on the unoccupied rows)",
                                         cmul * 2.0 * 2.0 * (ns - Nh) * Nh ** 2, tm["refresh_gemm"]["ms"], 2 * K,
                                         "k_gemm_W_dmma_dram_bytes_per_matrix", cmul * 2.0 * 2.0 * ns * Nh ** 2)
         cands += [roofline_inverse, roofline_gemm]

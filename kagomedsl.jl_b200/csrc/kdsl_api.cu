@@ -387,33 +387,33 @@ int launch_inverse_clc(kdsl_handle h, const int *list) {
 }
 
 // reevaluateW! as ONE cluster kernel (kdsl_reeval_cl.cuh); returns -1 when it does not apply.
-int launch_reeval_cl(kdsl_handle h, const int *list) {
-    if (!h->rcl_ok || h->cplx) return -1;
+template <int T, int MINB>
+int launch_reeval_cl_t(kdsl_handle h, const int *list) {
     const int cl = h->reeval_cluster;
-    if (cl < 2 || cl > 8) return -1;
-    constexpr int NB = 24, DG = 4;
+    constexpr int NB = 24, DG = 4, NWARPS = T / 32;
     const int NG = cl - 1;
+    if (h->rcl_NpMax > 4 * NWARPS * 8 || h->rcl_NpMax > T) return -1;   // row tiles of the next-panel update; thread = row
     // X slots (column tiles) a CTA needs: its pairs of the first block step, its V tiles of the last step, one panel
     const int pairs0 = (h->rcl_ntcMax + 1) / 2;
     const int XT = std::max(std::max(2 * ((pairs0 + NG - 1) / NG), (h->rcl_nvtMax + cl - 1) / cl + 1), NB / 8);
     const int nv = (h->rcl_nvtMax + cl - 1) / cl + 1;
-    if (nv > 32) return -1;                               // 16 warps x 2 column tiles in the last step
+    if (nv > 2 * NWARPS) return -1;                       // two column tiles per warp in the last step
     const int SW = 8 * nv;
     const size_t smem = reeval_cl_smem(NB, h->rcl_NpMax, h->rcl_CpMax, h->S.ns, XT, SW);
-    if (smem > (size_t)227 * 1024) return -1;
-    auto kern = k_reeval_cl<NB, DG>;
+    if (MINB * (smem + 1024) > (size_t)227 * 1024) return -1;
+    auto kern = k_reeval_cl<NB, DG, T, MINB>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.gridDim = dim3(cl * (h->num_sms / cl));
+    cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cl * (MINB * h->num_sms / cl));
     int ncl = 0;
     CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
     if (ncl < 1) return -1;
-    ncl = std::min(ncl, h->num_sms / cl);
-    if (getenv("KDSL_DEBUG_OCC")) fprintf(stderr, "k_reeval_cl: cluster size %d, %d active clusters, smem %zu, XT %d\n", cl, ncl, smem, XT);
+    ncl = std::min(ncl, MINB * h->num_sms / cl);
+    if (getenv("KDSL_DEBUG_OCC")) fprintf(stderr, "k_reeval_cl<%d,%d>: cluster size %d, %d active clusters, smem %zu, XT %d\n", T, MINB, cl, ncl, smem, XT);
     if (!h->rcl_scratch || h->rcl_scratch_clusters < ncl) {
         int rc = dev_alloc(h, &h->rcl_scratch, (size_t)ncl * reeval_cl_scratch_doubles(NB, h->rcl_NpMax, h->rcl_CpMax));
         if (rc) return rc;
@@ -425,6 +425,15 @@ int launch_reeval_cl(kdsl_handle h, const int *list) {
                           h->Np_up, h->Np_dn, h->rcl_NpMax, h->rcl_CpMax, XT, SW, rs));
     CK(cudaGetLastError());
     return KDSL_OK;
+}
+int launch_reeval_cl(kdsl_handle h, const int *list) {
+    if (!h->rcl_ok || h->cplx) return -1;
+    if (h->reeval_cluster < 2 || h->reeval_cluster > 8) return -1;
+    if (h->rcl_NpMax <= 256 && (h->inverse_tuning & 15) != 1) {          // two 256-thread CTAs per SM: twice the matrices in flight
+        const int rc = launch_reeval_cl_t<256, 2>(h, list);
+        if (rc >= 0) return rc;
+    }
+    return launch_reeval_cl_t<512, 1>(h, list);
 }
 
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {

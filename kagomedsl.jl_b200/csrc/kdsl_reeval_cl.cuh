@@ -73,11 +73,11 @@ __host__ __device__ inline size_t reeval_cl_scratch_doubles(int NB, int NpMax, i
 
 // ---- item set-up, all threads of every CTA: context and the column -> site tables (tilde_U^T columns in label order, then
 //      the unoccupied sites in ascending order) ----
-template <int NB>
+template <int NB, int T>
 __device__ __noinline__ void rcl_setup(RclShared *H, const DevState &S, const int *__restrict__ list, const double *UT_up,
                                         const double *UT_dn, int *__restrict__ status, int Np_up, int Np_dn, int item) {
     const RclArrays<NB> L(H);
-    constexpr int T = 512, NWARPS = 16;
+    constexpr int NWARPS = T / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = item >> 1, spin = item & 1;
     const int w = list ? list[b] : b;
@@ -282,10 +282,10 @@ __device__ __forceinline__ void rcl_gather_one(RclShared *H, const RclArrays<NB>
 
 // ---- P, all 16 warps: the kn columns of the next panel (from column k1) with the operands of step s (sM, sPivRow, kw pivots).
 //      Item = row tile; a warp owns row tiles warp, warp + 16, ... (at most NI = 4: Np <= 512) and loads them all up front. ----
-template <int NB, bool FIRST>
+template <int NB, bool FIRST, int T>
 __device__ __noinline__ void rcl_next_panel(RclShared *H, int k1, int kn, int kw) {
     const RclArrays<NB> L(H);
-    constexpr int KS = NB / 4, NT = NB / 8, NWARPS = 16, NI = 4, T = 512;
+    constexpr int KS = NB / 4, NT = NB / 8, NWARPS = T / 32, NI = 4;   // NI * NWARPS row tiles: Np <= 512 (T = 512), 256 (T = 256)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gr = lane >> 2, tg = lane & 3;
     const int Np = H->Np, Cp = H->Cp;
@@ -341,10 +341,9 @@ __device__ __noinline__ void rcl_next_panel(RclShared *H, int k1, int kn, int kw
 }
 
 // ---- G: operands and pivot rows of step s: scratch -> shared memory ----
-template <int NB>
+template <int NB, int T>
 __device__ __noinline__ void rcl_load_operands(RclShared *H, int s) {
     const RclArrays<NB> L(H);
-    constexpr int T = 512;
     const int tid = threadIdx.x;
     const double2 *src = reinterpret_cast<const double2 *>(H->Mg + (size_t)(s & 1) * NB * H->NpMax);
     double2 *dst = reinterpret_cast<double2 *>(L.sM);
@@ -356,10 +355,10 @@ __device__ __noinline__ void rcl_load_operands(RclShared *H, int s) {
 // ---- G: block step with the operands in sM: the unfinished column tiles [tf, Cp / 8) in pairs; pair pi (tiles 2 pi, 2 pi + 1)
 //      belongs to G CTA (pi - tf / 2) mod NG and sits in X slots 2 li, 2 li + 1 (li = its local index).  First the raw pivot rows
 //      of my columns, then items = (pair, row slice) over the 16 warps.  D row tiles of loads in flight per warp. ----
-template <int NB, int D, bool FIRST>
+template <int NB, int D, bool FIRST, int T>
 __device__ __noinline__ void rcl_update(RclShared *H, int tf, int kw) {
     const RclArrays<NB> L(H);
-    constexpr int KS = NB / 4, CT = 2, T = 512, NWARPS = 16;
+    constexpr int KS = NB / 4, CT = 2, NWARPS = T / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gr = lane >> 2, tg = lane & 3;
     const int Np = H->Np, Cp = H->Cp, NG = H->NG, grank = H->rank - 1, RS = H->RS;
@@ -453,10 +452,10 @@ __device__ __noinline__ void rcl_update(RclShared *H, int tf, int kw) {
 //      two) column tiles, deposits the 8 x 16 results in the stage; after a barrier the CTA writes its site range of the 8
 //      finished columns of W (row rt*8 + r of B is column sStep[..] of W; thread = site; unit rows of the occupied sites
 //      filled in on the way). ----
-template <int NB, int D, bool FIRST>
+template <int NB, int D, bool FIRST, int T>
 __device__ __noinline__ void rcl_last_step(RclShared *H, int kw, int nwk) {
     const RclArrays<NB> L(H);
-    constexpr int KS = NB / 4, CT = 2, T = 512;
+    constexpr int KS = NB / 4, CT = 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gr = lane >> 2, tg = lane & 3;
     const int Np = H->Np, Cp = H->Cp, N = H->N, M = H->M, ns = H->ns, wl = H->rank;
@@ -545,8 +544,8 @@ __device__ __noinline__ void rcl_last_step(RclShared *H, int kw, int nwk) {
 #undef RCL_TILE
 }
 
-template <int NB, int DG>
-__global__ void __launch_bounds__(512, 1)
+template <int NB, int DG, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 k_reeval_cl(DevState S, const int *__restrict__ list, double *__restrict__ scratch, const double *__restrict__ UT_up,
             const double *__restrict__ UT_dn, int *__restrict__ status, int Np_up, int Np_dn, int NpMax, int CpMax,
             int XT, int SW, int RS) {
@@ -556,6 +555,7 @@ k_reeval_cl(DevState S, const int *__restrict__ list, double *__restrict__ scrat
     const int tid = threadIdx.x;
     const int rank = (int)cl_ctarank(), CL = (int)cl_nctarank();
     const bool isP = rank == 0;
+    if (tid < 16) H->sKey[tid] = 0u;                        // (keys of warps that do not exist never win)
     if (tid == 0) {
         H->NpMax = NpMax; H->CpMax = CpMax; H->ns = S.ns; H->XT = XT; H->SW = SW; H->NG = CL - 1; H->rank = rank; H->RS = RS;
         double *base = scratch + (size_t)cl_clusterid() * reeval_cl_scratch_doubles(NB, NpMax, CpMax);
@@ -567,7 +567,7 @@ k_reeval_cl(DevState S, const int *__restrict__ list, double *__restrict__ scrat
     __syncthreads();
     const int n_items = 2 * batch_count(S, list);
     for (int item = (int)cl_clusterid(); item < n_items; item += (int)cl_nclusterid()) {
-        rcl_setup<NB>(H, S, list, UT_up, UT_dn, status, Np_up, Np_dn, item);
+        rcl_setup<NB, T>(H, S, list, UT_up, UT_dn, status, Np_up, Np_dn, item);
         const int Np = H->Np;
         bool pivoted = false;                               // P: my row has been a pivot
         long long t_phase = PHASE_CLOCK();
@@ -584,28 +584,28 @@ k_reeval_cl(DevState S, const int *__restrict__ list, double *__restrict__ scrat
             const bool first = s == 0;
             if (kn > 0) {
                 if (isP) {
-                    if (first) rcl_next_panel<NB, true>(H, k1, kn, kw);
-                    else rcl_next_panel<NB, false>(H, k1, kn, kw);
+                    if (first) rcl_next_panel<NB, true, T>(H, k1, kn, kw);
+                    else rcl_next_panel<NB, false, T>(H, k1, kn, kw);
                     __syncthreads();
                     CL_TICK(0, 0);
                     pivoted = rcl_factor_panel<NB, false>(H, k1, kn, (s + 1) & 1, pivoted);
                     CL_TICK(0, 1);
                 } else {
-                    rcl_load_operands<NB>(H, s);
+                    rcl_load_operands<NB, T>(H, s);
                     __syncthreads();
                     CL_TICK(1, 3);
-                    if (first) rcl_update<NB, DG, true>(H, (k1 + kn) >> 3, kw);
-                    else rcl_update<NB, DG, false>(H, (k1 + kn) >> 3, kw);
+                    if (first) rcl_update<NB, DG, true, T>(H, (k1 + kn) >> 3, kw);
+                    else rcl_update<NB, DG, false, T>(H, (k1 + kn) >> 3, kw);
                     CL_TICK(1, 5);
                 }
             } else {
                 if (!isP) {
-                    rcl_load_operands<NB>(H, s);
+                    rcl_load_operands<NB, T>(H, s);
                     __syncthreads();
                     CL_TICK(1, 3);
                 }
-                if (first) rcl_last_step<NB, 4, true>(H, kw, CL);
-                else rcl_last_step<NB, 4, false>(H, kw, CL);
+                if (first) rcl_last_step<NB, 4, true, T>(H, kw, CL);
+                else rcl_last_step<NB, 4, false, T>(H, kw, CL);
                 CL_TICK(0, 0);
                 CL_TICK(1, 4);
             }

@@ -530,6 +530,11 @@ k_gemm_W_dmma(DevState S, const int *__restrict__ list, const double *__restrict
     PHASE_TICK(7);
 }
 
+// (A 3-warp, 72 x 24 tile version of this kernel -- the layout of the ComplexF64 product k_gemm_W_dmma_c, which reaches 63 % of
+// the DMMA peak -- was measured SLOWER here: 28.1 ms against 22.6 ms per 2048-walker bin at 972 sites.  A real block product
+// has a quarter of the complex one's arithmetic per operand byte, and the narrow tile re-reads the gathered rows of U three
+// times as often.)
+
 #ifdef KDSL_DEV_VARIANTS   // superseded kernels: built only with `make DEV=1`, not part of the product library
 // cp.async version of k_gemm_W_dmma (gemm_variant 0): the operands go global -> shared memory directly (LDGSTS, 8 bytes
 // per element with zero fill), STAGES stages deep, so no register staging, one barrier per stage and loads in flight
