@@ -139,14 +139,15 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
                     } else {
                         const int wq = 15 - (int)(bk & 15u);
                         if (warp == wq && leader) {
+                            // the leader publishes its RAW row and 1 / pivot; the scaling by 1 / pivot is done by every
+                            // thread for itself (one complex product more per thread, sixteen fewer on the serial path)
                             const double rinv = rcp_fast(n2);        // 1 / z = conj(z) / |z|^2
-                            const cplx pinv = c_make(ar[k] * rinv, -(ai[k] * rinv));
                             sIdx[0] = tid;
                             sPivRow[k] = tid;
-                            *reinterpret_cast<double2 *>(sRinv) = pinv;
+                            *reinterpret_cast<double2 *>(sRinv) = c_make(ar[k] * rinv, -(ai[k] * rinv));
                             double2 *dst = reinterpret_cast<double2 *>(sRow);
 #pragma unroll
-                            for (int j = 0; j < NB; j++) dst[j] = c_mul(c_make(ar[j], ai[j]), pinv);
+                            for (int j = 0; j < NB; j++) dst[j] = c_make(ar[j], ai[j]);
                         }
                         __syncthreads();
                         const int p = sIdx[0];
@@ -159,15 +160,15 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
                                 gstep = k0 + k;
 #pragma unroll
                                 for (int j = 0; j < NB; j++) {
-                                    const cplx v = j == k ? pinv : prow[j];
+                                    const cplx v = j == k ? pinv : c_mul(c_make(ar[j], ai[j]), pinv);
                                     ar[j] = v.x;
                                     ai[j] = v.y;
                                 }
                             } else {
-                                const cplx f = c_make(-ar[k], -ai[k]);
+                                const cplx f = c_mul(c_make(-ar[k], -ai[k]), pinv);   // -a[k] / pivot
 #pragma unroll
                                 for (int j = 0; j < NB; j++) {
-                                    const cplx v = j == k ? c_mul(f, pinv) : c_fma(f, prow[j], c_make(ar[j], ai[j]));
+                                    const cplx v = j == k ? f : c_fma(f, prow[j], c_make(ar[j], ai[j]));
                                     ar[j] = v.x;
                                     ai[j] = v.y;
                                 }

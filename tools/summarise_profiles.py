@@ -53,8 +53,13 @@ def main():
              "inverse": ("k_inverse_v4_dram_bytes_per_matrix", 1024), "gemm": ("k_gemm_W_dmma_dram_bytes_per_matrix", 2048),
              "flush": ("k_flush_wb_dram_bytes_per_walker_flush", None),
              # 972 sites (tools/capture_profiles_r2.sh B: prof_refresh.py 18 512 -> 512 matrices per inverse launch, 1024 per product launch)
-             "inverse972": ("k_inverse_v4_dram_bytes_per_matrix_972", 512), "gemm972": ("k_gemm_W_dmma_dram_bytes_per_matrix_972", 1024)}
-    for name in ("fused", "inverse", "gemm", "flush", "decide", "measure", "gather", "resident", "inverse972", "gemm972", "flush972", "flushc"):
+             "inverse972": ("k_inverse_v4_dram_bytes_per_matrix_972", 512), "gemm972": ("k_gemm_W_dmma_dram_bytes_per_matrix_972", 1024),
+             # session 3 (tools/capture_profiles_r3.sh): the initial refresh of quick_bench's 4096 ComplexF64 walkers (both species
+             # in one launch); prof_refresh.py 18 512 -> 1024 matrices per cluster-inverse launch
+             "invclc": ("k_inverse_cl_c_dram_bytes_per_walker_refresh", 4096), "gemmc": ("k_gemm_W_dmma_c_dram_bytes_per_walker_refresh", 4096),
+             "invcl972": ("k_inverse_cl_dram_bytes_per_matrix_972", 1024)}
+    for name in ("fused", "inverse", "gemm", "flush", "decide", "measure", "gather", "resident", "inverse972", "gemm972", "flush972", "flushc",
+                 "invclc", "gemmc", "flushdc", "invcl972"):
         rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (name, TAG))
         if not os.path.exists(rep):
             print("missing", rep)
