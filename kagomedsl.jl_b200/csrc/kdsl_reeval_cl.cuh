@@ -1,5 +1,7 @@
-// kdsl_reeval_cl.cuh -- reevaluateW! (src/MonteCarlo.jl:55-66) + tilde_U (src/MonteCarlo.jl:92-115) for 256 < Np <= 512
-// (972 sites: N = 486) as ONE kernel over THREAD-BLOCK CLUSTERS: the mathematics of k_reeval_fused (Gauss-Jordan with implicit
+// kdsl_reeval_cl.cuh -- reevaluateW! (src/MonteCarlo.jl:55-66) + tilde_U (src/MonteCarlo.jl:92-115) for Np <= 512
+// (built for 972 sites: N = 486; inverse_variant 8) as ONE kernel over THREAD-BLOCK CLUSTERS.  Measured:
+// slower than cluster inverse + product at 972 sites (68 ms vs 59 ms per 2048-walker bin) and slower than the one-CTA
+// k_reeval_fused at 432 sites (25.8 ms vs 16.3 ms with two 256-thread CTAs per SM), so it is a selectable variant only: the mathematics of k_reeval_fused (Gauss-Jordan with implicit
 // row pivoting on B = [tilde_U^T | V^T], N x (N + M); the V^T columns end as the non-trivial rows of W; finished tilde_U^T
 // columns are dropped: N^3 + 2 N^2 M = 3 N^3 flop instead of inverse + product = 4 N^3) with the work split of k_inverse_cl:
 //
