@@ -141,6 +141,24 @@ def test_replay_c128_8x8_landau_level(kd):
     assert acc[kd._lib.ACC_N_REFRESH] >= 3
 
 
+@pytest.mark.parametrize("options", [{}, {"inverse_variant": 7, "flush_variant": 4, "gemm_variant": 4}])
+def test_replay_c128_432_sites(kd, options):
+    """ComplexF64 engine at the headline lattice (12x12, 432 sites, Peierls flux): N = 216 runs the production instantiations
+    of the complex tensor-pipe kernels -- k_inverse_cl_c with panels of 16 columns and two CTAs per SM, k_gemm_W_dmma_c with
+    3 x 9 tiles, k_flush_dmma_c with two 216-row blocks -- against the c128 oracle: 3 walkers x 450 replayed sweeps across the
+    re-evaluations at sweeps 216 and 432; two walkers driven at ~3x the acceptance rate so that the flush runs often.
+    Second case: the embedding inverse, the FMA flush and the FMA product on the same stream."""
+    lat, ham = U.problem(12, 12, (True, True), (True, False), "pi", None, 0.02)
+    assert np.iscomplexobj(ham.U_up) and np.abs(np.asarray(ham.U_up).imag).max() > 1e-3
+    ns, nw, n = kd.ns(lat), 3, 450
+    ku, kdn = chain_states(kd, ham, ns, ns // 2, nw, 2000, 11)
+    rng = np.random.default_rng(4320)
+    r = rng.random((n, nw)) * np.array([1.0, 0.45, 0.45])
+    bond = rng.integers(1, len(ham.nn) + 1, size=(n, nw)).astype(np.int32)
+    acc, tm = replay_against_oracle(kd, ham, ku, kdn, r, bond, (1, 215, 1, 120, 113), options, dtype="c128")
+    assert acc[kd._lib.ACC_N_REFRESH] >= 2 and tm["update"]["flushes"] >= 3
+
+
 def test_measure_right_after_refresh_432_and_two_handles(kd):
     """Regression: set_config -> refresh -> measure as the FIRST calls on a handle at 432 sites (k_measure_wb needs 92 KB
     of dynamic shared memory; the opt-in used to be set inside the first flush launch, process-wide), and a second
