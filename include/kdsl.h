@@ -236,12 +236,12 @@ int kdsl_reset_timers(kdsl_handle h);
  * "inverse_variant": how reevaluateW! (src/MonteCarlo.jl:55-66) is computed -- 0 (default) / 6 = the one-kernel
  * re-evaluation k_reeval_fused when it applies (N <= 256 per species, ns <= 512), else gather + cluster inverse
  * k_inverse_cl (one matrix per thread-block cluster, 256 < N <= 512; 7 forces it) + DMMA product; 5 / 4 = gather +
- * one-CTA blocked implicit-pivoting inverse (with / without look-ahead) + DMMA product; 8 = the cluster re-evaluation
- * k_reeval_cl (one kernel, N <= 512); 1 = simple cross-check kernels.  ComplexF64 engine: 0 (default) / 9 = complex
+ * one-CTA blocked implicit-pivoting inverse (with / without look-ahead) + DMMA product; 1 = simple cross-check kernels;
+ * (8 = the cluster re-evaluation k_reeval_cl, one kernel for N <= 512: `make DEV=1` builds only, measured slower).  ComplexF64 engine: 0 (default) / 9 = complex
  * cluster inverse on split (re, im) planes + tensor-pipe product, 4 / 5 / 7 = blocked inverse of the real 2N x 2N
  * embedding, 1 = unblocked complex elimination; "flush_variant" 0 = tensor-pipe flush, 4 = FMA flush.
- * "inverse_cluster" / "reeval_cluster" (CTAs per matrix of the cluster kernels, 2..8), "inverse_row_slices" /
- * "reeval_rs", "inverse_tuning", "gemm_variant", "fused_ctas": developer knobs.  The superseded variants (update_variant 1,
+ * "inverse_cluster" (CTAs per matrix of the cluster kernels, 2..8), "inverse_row_slices", "inverse_tuning",
+ * "gemm_variant", "fused_ctas": developer knobs.  The superseded variants (update_variant 1,
  * flush_variant 1, inverse_variant 2 / 3, gemm_variant 2 / 3) exist only in a `make DEV=1` build.
  * KDSL_ERR_INVALID_ARGUMENT if the name is unknown or the value is not available in this build. */
 int kdsl_set_option(kdsl_handle h, const char *name, int64_t value);

@@ -21,7 +21,9 @@
 #include "kdsl_inverse_v4.cuh"
 #include "kdsl_inverse_v5.cuh"
 #include "kdsl_inverse_cl.cuh"
-#include "kdsl_reeval_cl.cuh"
+#ifdef KDSL_DEV_VARIANTS
+#include "kdsl_reeval_cl.cuh"   // cluster re-evaluation: measured slower than the product paths everywhere
+#endif
 #include "kdsl_inverse_cl_c.cuh"
 #include "kdsl_reeval_fused.cuh"
 #ifdef KDSL_DEV_VARIANTS   // superseded kernels kept for A/B measurements: `make DEV=1` (not in the product library)
@@ -386,6 +388,7 @@ int launch_inverse_clc(kdsl_handle h, const int *list) {
     return launch_inverse_clc_t<8, 2, 512, 1>(h, list);
 }
 
+#ifdef KDSL_DEV_VARIANTS
 // reevaluateW! as ONE cluster kernel (kdsl_reeval_cl.cuh); returns -1 when it does not apply.
 template <int T, int MINB>
 int launch_reeval_cl_t(kdsl_handle h, const int *list) {
@@ -435,6 +438,8 @@ int launch_reeval_cl(kdsl_handle h, const int *list) {
     }
     return launch_reeval_cl_t<512, 1>(h, list);
 }
+
+#endif  // KDSL_DEV_VARIANTS
 
 int launch_inverse(kdsl_handle h, const int *list, double *A, int spin, int Np) {
     if ((h->inverse_variant == 0 || h->inverse_variant == 5) && Np <= 256) {
@@ -609,6 +614,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
         h->t_launch[KDSL_T_REFRESH_INVERSE] += 1;
         return KDSL_OK;
     }
+#ifdef KDSL_DEV_VARIANTS
     if (h->inverse_variant == 8 && h->rcl_ok) {
         // one cluster kernel for 256 < Np <= 512 (kdsl_reeval_cl.cuh)
         Span sp(h, KDSL_T_REFRESH_INVERSE);
@@ -620,6 +626,7 @@ int launch_refresh(kdsl_handle h, const int *list) {
         h->t_launch[KDSL_T_REFRESH_INVERSE] += 1;
         return KDSL_OK;
     }
+#endif
     const bool fast = h->inverse_variant != 1;
     {
         Span sp(h, KDSL_T_REFRESH_GATHER);
@@ -1131,6 +1138,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             CKD(cudaStreamSynchronize(h->stream));
         }
     }
+#ifdef KDSL_DEV_VARIANTS
     if (!cplx && std::max(h->Np_up, h->Np_dn) <= 512 && std::min(h->Np_up, h->Np_dn) >= 8) {
         // cluster re-evaluation (k_reeval_cl; the default for 256 < Np <= 512, inverse_variant 8 forces it on smaller lattices):
         // transposed U with padding rows (shared with k_reeval_fused); the workspaces are allocated at the first launch
@@ -1148,6 +1156,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
         }
         h->rcl_ok = true;
     }
+#endif
 #undef ALLOC
     // default xoshiro states must not be all-zero: seed walker w with a fixed SplitMix64 stream
     {
@@ -1693,6 +1702,9 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     } else if (n == "inverse_variant") {
 #ifndef KDSL_DEV_VARIANTS
         if (value == 2 || value == 3) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+#endif
+#ifndef KDSL_DEV_VARIANTS
+        if (value == 8) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant 8 (cluster re-evaluation) is a developer variant (build with make DEV=1)");
 #endif
         if (value < 0 || value > 9 || (value == 9 && !h->cplx)) return fail(KDSL_ERR_INVALID_ARGUMENT, "inverse_variant must be 0, 1, 4, 5, 6, 7 or 8 (9: ComplexF64 engine only)");
         h->inverse_variant = (int)value;

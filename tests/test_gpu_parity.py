@@ -104,7 +104,11 @@ def test_cluster_reeval_matches_oracle(kd, n1, n2, N_up, cluster, row_slices, nw
     rng = np.random.default_rng(300 + n1 + cluster)
     ku, kdn = U.well_conditioned_mott(rng, ham, ns, ham.N_up, nw, cond_max=1e5)
     eng = kd.Engine(ham, nw)
-    eng.set_option("inverse_variant", 8)
+    try:
+        eng.set_option("inverse_variant", 8)
+    except kd.KdslError:
+        eng.close()
+        pytest.skip("k_reeval_cl is a developer variant (make DEV=1): measured slower than the product paths, DESIGN.md 4.6")
     eng.set_option("reeval_cluster", cluster)
     eng.set_option("reeval_rs", row_slices)
     eng.set_config(ku, kdn)
@@ -134,7 +138,11 @@ def test_cluster_inverse_singular_matrix_is_flagged(kd, variant):
     expect_bad = np.array([kdn[w, bad_sites[0]] != 0 for w in range(nw)])
     assert expect_bad[7] and not expect_bad.all()
     eng = kd.Engine(ham2, nw)
-    eng.set_option("inverse_variant", variant)
+    try:
+        eng.set_option("inverse_variant", variant)
+    except kd.KdslError:
+        eng.close()
+        pytest.skip("developer variant (make DEV=1)")
     eng.set_config(ku, kdn)
     with pytest.raises(kd.SingularException):
         eng.refresh()
