@@ -343,7 +343,7 @@ bool inverse_clc_applies(kdsl_handle h) {
     if (NpMax > 512 || std::min(h->Npc_up, h->Npc_dn) < 8) return false;
     // the split planes live in the embedding's workspace: 2 Npc^2 <= Np^2 doubles per entry
     if ((size_t)2 * h->Npc_up * h->Npc_up > (size_t)h->Np_up * h->Np_up || (size_t)2 * h->Npc_dn * h->Npc_dn > (size_t)h->Np_dn * h->Np_dn) return false;
-    return inverse_clc_smem(16, NpMax) <= (size_t)227 * 1024;
+    return inverse_clc_smem(8, NpMax) <= (size_t)227 * 1024;     // (panels of 16 columns are used when two CTAs per SM fit)
 }
 template <int NB, int CT, int T, int MINB>
 int launch_inverse_clc_t(kdsl_handle h, const int *list) {

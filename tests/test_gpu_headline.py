@@ -159,6 +159,35 @@ def test_replay_c128_432_sites(kd, options):
     assert acc[kd._lib.ACC_N_REFRESH] >= 2 and tm["update"]["flushes"] >= 3
 
 
+def test_c128_972_sites_refresh_and_rank1_path(kd):
+    """ComplexF64 engine at 18x18 (972 sites, N = 486 > 256): k_inverse_cl_c with 512-thread CTAs and panels of 8 columns,
+    k_gemm_W_dmma_c with 7 x 21 tiles; the Woodbury kernels' operands exceed the shared memory at this size, so the engine
+    falls back to the reference's immediate rank-1 update (documented).  W against numpy, then 60 device-RNG sweeps:
+    maintained W == re-evaluated W, incremental Z_mu == recount."""
+    lat, ham = U.problem(18, 18, (True, True), (True, False), "pi", None, 0.01)
+    ns, nw = kd.ns(lat), 3
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ns // 2)
+    eng = kd.Engine(ham, nw)
+    assert eng.is_complex
+    eng.set_config(ku0, kd0)
+    eng.set_rng(kd.walker_states(972, nw))
+    eng.refresh()
+    Uu, Ud = np.asarray(ham.U_up), np.asarray(ham.U_down)
+    assert U.relerr(eng.get_W(0, 0), Uu @ np.linalg.inv(kd.tilde_U(Uu, ku0))) < 1e-9
+    assert U.relerr(eng.get_W(2, 1), Ud @ np.linalg.inv(kd.tilde_U(Ud, kd0))) < 1e-9
+    eng.sweep(60, -1)
+    ku, kdn = eng.get_config()
+    z, zr = eng.Z()
+    assert np.array_equal(z, zr)
+    Wm = [eng.get_W(w, 0) for w in range(nw)]
+    assert any(not np.array_equal(ku[w], ku0) for w in range(nw))               # the chains moved
+    eng.refresh()
+    for w in range(nw):
+        Wr = Uu @ np.linalg.inv(kd.tilde_U(Uu, ku[w]))
+        assert U.relerr(eng.get_W(w, 0), Wr) < 1e-9 and U.relerr(Wm[w], Wr) < 1e-8
+    eng.close()
+
+
 def test_measure_right_after_refresh_432_and_two_handles(kd):
     """Regression: set_config -> refresh -> measure as the FIRST calls on a handle at 432 sites (k_measure_wb needs 92 KB
     of dynamic shared memory; the opt-in used to be set inside the first flush launch, process-wide), and a second
