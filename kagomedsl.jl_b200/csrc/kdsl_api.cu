@@ -154,11 +154,30 @@ int dev_alloc(kdsl_handle h, T **p, size_t n) {
     cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
     if (e != cudaSuccess)
         return fail(KDSL_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
-    e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+    // zero-fill ON THE ENGINE'S STREAM: that stream is non-blocking, so a memset on the legacy default stream would not be
+    // ordered with the kernels that use the buffer
+    e = h->stream ? cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream) : cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess && !h->stream) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return fail(KDSL_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     h->allocs.push_back(q);
     *p = static_cast<T *>(q);
     return KDSL_OK;
+}
+
+// Host <-> device copies go through the ENGINE'S stream and are complete when this returns.  A plain cudaMemcpy runs on the
+// legacy default stream, which a cudaStreamNonBlocking stream does not synchronise with -- and a pageable host-to-device
+// cudaMemcpy may return once its last chunk sits in the staging buffer, before the DMA has landed: a kernel launched on the
+// engine's stream right afterwards could read the old contents of the buffer's tail (seen as run-to-run differences of the
+// Z_mu of the last walkers of a 512-walker handle).
+cudaError_t copy_sync(kdsl_handle h, void *dst, const void *src, size_t n, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(h->stream);
+}
+cudaError_t memset_sync(kdsl_handle h, void *dst, int v, size_t n) {
+    cudaError_t e = cudaMemsetAsync(dst, v, n, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(h->stream);
 }
 
 int use_device(kdsl_handle h) {
@@ -1063,12 +1082,12 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             nbr[fill[hbi[b]]++] = hbj[b];
             nbr[fill[hbj[b]]++] = hbi[b];
         }
-        CKD(cudaMemcpy(bi, hbi.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(bj, hbj.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(adj_off, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(adj_nbr, nbr.data(), 2 * (size_t)n_bonds * sizeof(int), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(dUu, U_up, cz * ns * n_up * sizeof(double), cudaMemcpyHostToDevice));
-        CKD(cudaMemcpy(dUd, U_dn, cz * ns * n_dn * sizeof(double), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, bi, hbi.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, bj, hbj.data(), n_bonds * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, adj_off, off.data(), (ns + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, adj_nbr, nbr.data(), 2 * (size_t)n_bonds * sizeof(int), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, dUu, U_up, cz * ns * n_up * sizeof(double), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, dUd, U_dn, cz * ns * n_dn * sizeof(double), cudaMemcpyHostToDevice));
     }
     S.bi = bi; S.bj = bj; S.adj_off = adj_off; S.adj_nbr = adj_nbr; S.U_up = dUu; S.U_dn = dUd;
     ALLOC(S.kup, nw * ns); ALLOC(S.kdn, nw * ns);
@@ -1168,7 +1187,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
             v = z ^ (z >> 31);
         }
-        CKD(cudaMemcpy(S.rng, st.data(), st.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CKD(copy_sync(h, S.rng, st.data(), st.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
     CKD(cudaFuncSetAttribute(k_inverse_gj, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // Opt-in dynamic shared memory of the Woodbury kernels.  cudaFuncSetAttribute is per device (context), so this is
@@ -1332,8 +1351,8 @@ int kdsl_set_config(kdsl_handle h, const int32_t *kup, const int32_t *kdn) {
                             ku[R] != 0 ? "doubly occupied" : "unoccupied");
     }
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(S.kup, kup, (size_t)S.nw * S.ns * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(S.kdn, kdn, (size_t)S.nw * S.ns * sizeof(int), cudaMemcpyHostToDevice));
+    CK(copy_sync(h, S.kup, kup, (size_t)S.nw * S.ns * sizeof(int), cudaMemcpyHostToDevice));
+    CK(copy_sync(h, S.kdn, kdn, (size_t)S.nw * S.ns * sizeof(int), cudaMemcpyHostToDevice));
     k_count_Z<<<grid_for_warps(S.nw), 256, 0, h->stream>>>(S, nullptr, 1);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(S.cnt, 0, 8 * sizeof(int), h->stream));
@@ -1353,8 +1372,8 @@ int kdsl_get_config(kdsl_handle h, int32_t *kup, int32_t *kdn) {
     if (rc) return rc;
     if (!kup || !kdn) return fail(KDSL_ERR_INVALID_ARGUMENT, "null output");
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(kup, h->S.kup, (size_t)h->S.nw * h->S.ns * sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(kdn, h->S.kdn, (size_t)h->S.nw * h->S.ns * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(copy_sync(h, kup, h->S.kup, (size_t)h->S.nw * h->S.ns * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(copy_sync(h, kdn, h->S.kdn, (size_t)h->S.nw * h->S.ns * sizeof(int), cudaMemcpyDeviceToHost));
     return KDSL_OK;
 }
 
@@ -1366,7 +1385,7 @@ int kdsl_set_rng(kdsl_handle h, const uint64_t *states) {
         if (!(states[4 * w] | states[4 * w + 1] | states[4 * w + 2] | states[4 * w + 3]))
             return fail(KDSL_ERR_INVALID_ARGUMENT, "walker %d: all-zero Xoshiro state", w);
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(h->S.rng, states, (size_t)h->S.nw * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(copy_sync(h, h->S.rng, states, (size_t)h->S.nw * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice));
     return KDSL_OK;
 }
 
@@ -1375,7 +1394,7 @@ int kdsl_get_rng(kdsl_handle h, uint64_t *states) {
     if (rc) return rc;
     if (!states) return fail(KDSL_ERR_INVALID_ARGUMENT, "states is null");
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(states, h->S.rng, (size_t)h->S.nw * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(copy_sync(h, states, h->S.rng, (size_t)h->S.nw * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return KDSL_OK;
 }
 
@@ -1526,10 +1545,10 @@ int kdsl_set_observables(kdsl_handle h, int nq, const double *cos_qr, const doub
     CK(renew(&h->d_obs, 4 + 2 * (size_t)nq));
     CK(renew(&S.obs_w, nw * (4 + 2 * (size_t)nq)));
     if (nq > 0) {
-        CK(cudaMemcpy(h->d_qcos, cos_qr, (size_t)nq * ns * sizeof(double), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->d_qsin, sin_qr, (size_t)nq * ns * sizeof(double), cudaMemcpyHostToDevice));
+        CK(copy_sync(h, h->d_qcos, cos_qr, (size_t)nq * ns * sizeof(double), cudaMemcpyHostToDevice));
+        CK(copy_sync(h, h->d_qsin, sin_qr, (size_t)nq * ns * sizeof(double), cudaMemcpyHostToDevice));
     }
-    CK(cudaMemset(S.obs_w, 0, nw * (4 + 2 * (size_t)nq) * sizeof(double)));
+    CK(memset_sync(h, S.obs_w, 0, nw * (4 + 2 * (size_t)nq) * sizeof(double)));
     S.q_cos = h->d_qcos; S.q_sin = h->d_qsin; S.nq = nq; S.obs_on = 1;
     return KDSL_OK;
 }
@@ -1544,7 +1563,7 @@ int kdsl_get_W(kdsl_handle h, int walker, int spin, double *out) {
     const double *src = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N * (h->cplx ? 2 : 1);
     if ((h->update_variant == 1 || h->update_variant == 2) && (rc = launch_flush(h, true))) return rc;   // fold pending delayed factors into W0
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out, src, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyDeviceToHost));
+    CK(copy_sync(h, out, src, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyDeviceToHost));
     return KDSL_OK;
 }
 
@@ -1557,7 +1576,7 @@ int kdsl_set_W(kdsl_handle h, int walker, int spin, const double *in) {
     double *dst = (spin ? S.W_dn : S.W_up) + (size_t)walker * S.ns * N * (h->cplx ? 2 : 1);
     if ((h->update_variant == 1 || h->update_variant == 2) && (rc = launch_flush(h, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(dst, in, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyHostToDevice));
+    CK(copy_sync(h, dst, in, (size_t)S.ns * N * sizeof(double) * (h->cplx ? 2 : 1), cudaMemcpyHostToDevice));
     return KDSL_OK;
 }
 
@@ -1638,7 +1657,7 @@ int kdsl_timers(kdsl_handle h, double *ms, int64_t *launches, int64_t *update_mo
     if (launches) memcpy(launches, h->t_launch, sizeof h->t_launch);
     if (update_moves) {
         unsigned long long v[2] = {0, 0};
-        CK(cudaMemcpy(v, h->S.upd_moves, sizeof v, cudaMemcpyDeviceToHost));
+        CK(copy_sync(h, v, h->S.upd_moves, sizeof v, cudaMemcpyDeviceToHost));
         update_moves[0] = (int64_t)v[0];
         update_moves[1] = (int64_t)v[1];
     }
@@ -1651,7 +1670,7 @@ int kdsl_reset_timers(kdsl_handle h) {
     if ((rc = flush_spans(h))) return rc;
     memset(h->t_ms, 0, sizeof h->t_ms);
     memset(h->t_launch, 0, sizeof h->t_launch);
-    CK(cudaMemset(h->S.upd_moves, 0, 4 * sizeof(unsigned long long)));
+    CK(memset_sync(h, h->S.upd_moves, 0, 4 * sizeof(unsigned long long)));
     return KDSL_OK;
 }
 

@@ -188,6 +188,40 @@ def test_c128_972_sites_refresh_and_rank1_path(kd):
     eng.close()
 
 
+def test_chains_are_reproducible_and_Z_is_right_for_every_handle_size(kd):
+    """Regression (round 2): host-to-device copies used to run on the legacy default stream while the engine's stream is
+    non-blocking; the kernel that counts Z_mu after set_config could start before the tail of the kappa upload had landed.
+    A 512-walker handle at 432 sites showed it: Z_mu of the last walkers wrong, chains different from run to run.  All
+    copies now go through the engine's stream.  Two runs must agree bit for bit, Z_mu must equal the recount right after
+    set_config, and a handle of 512 walkers must reproduce walkers 0..511 of a 1024-walker handle."""
+    lat, ham = U.problem(12, 12)
+    ns = kd.ns(lat)
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ns // 2)
+    states = kd.walker_states(1234, 1024)
+
+    def run(nw):
+        eng = kd.Engine(ham, nw)
+        eng.set_config(ku0, kd0)
+        z, zr = eng.Z()
+        assert np.array_equal(z, zr) and np.all(z == z[0])
+        eng.set_rng(states[:nw])
+        eng.refresh()
+        eng.sweep(120, -1)
+        ku, kdn = eng.get_config()
+        z, zr = eng.Z()
+        assert np.array_equal(z, zr)
+        rng = eng.get_rng()
+        eng.close()
+        return ku, kdn, rng
+
+    a = run(512)
+    for _ in range(3):
+        b = run(512)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    c = run(1024)
+    assert all(np.array_equal(x, y[:512]) for x, y in zip(a, c))
+
+
 def test_measure_right_after_refresh_432_and_two_handles(kd):
     """Regression: set_config -> refresh -> measure as the FIRST calls on a handle at 432 sites (k_measure_wb needs 92 KB
     of dynamic shared memory; the opt-in used to be set inside the first flush launch, process-wide), and a second
