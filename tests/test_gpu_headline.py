@@ -222,6 +222,40 @@ def test_chains_are_reproducible_and_Z_is_right_for_every_handle_size(kd):
     assert all(np.array_equal(x, y[:512]) for x, y in zip(a, c))
 
 
+def test_full_batch_4096_walkers_at_432_sites_matches_oracle_chains(kd):
+    """BASELINE's full single-GPU batch (4096 walkers x 432 sites, device Xoshiro streams, 450 sweeps across the
+    re-evaluations at sweeps 216 and 432): eight walkers picked across the batch (first, last, CTA and list boundaries)
+    must be bit-identical to the oracle's Carlo loop started from the same state -- kappa, acceptance count, O_L sum --
+    and every walker's incremental Z_mu must equal the recount.  (The small replay tests cannot see effects that need a
+    full machine: thousands of (walker, species) items per persistent CTA, hundreds of flushes per launch.)"""
+    lat, ham = U.problem(12, 12)
+    ns, nw, n = kd.ns(lat), 4096, 450
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ns // 2)
+    states = kd.walker_states(2026, nw)
+    eng = kd.Engine(ham, nw)
+    eng.set_config(ku0, kd0)
+    eng.set_rng(states)
+    eng.refresh()
+    eng.sweep(n, thermalization=100)
+    gku, gkd = eng.get_config()
+    z, zr = eng.Z()
+    assert np.array_equal(z, zr)
+    acc, acc_w, ol_w = eng.accumulators(per_walker=True)
+    assert acc[kd._lib.ACC_N_SINGULAR] == 0
+    for w in (0, 7, 8, 1023, 2048, 3333, 4094, 4095):
+        mc = U.O.MC(np.asarray(ham.nn, dtype=np.int32), ham.U_up, ham.U_down, "f64")
+        mc.set_kappa(ku0, kd0)
+        mc.reevaluateW()
+        st, _ = mc.run(U.O.Xoshiro(states[w]), n, 100)
+        oku, okd = mc.kappa()
+        assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd), f"walker {w}: configuration differs from the oracle chain"
+        assert acc_w[w] == st[0]
+        assert abs(ol_w[w] - st[1]) <= 1e-9 * max(1.0, abs(st[1]))
+        Wu, Wd = mc.W()
+        assert U.relerr(eng.get_W(w, 0), Wu) < TOL and U.relerr(eng.get_W(w, 1), Wd) < TOL
+    eng.close()
+
+
 def test_measure_right_after_refresh_432_and_two_handles(kd):
     """Regression: set_config -> refresh -> measure as the FIRST calls on a handle at 432 sites (k_measure_wb needs 92 KB
     of dynamic shared memory; the opt-in used to be set inside the first flush launch, process-wide), and a second
