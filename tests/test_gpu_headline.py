@@ -222,31 +222,40 @@ def test_chains_are_reproducible_and_Z_is_right_for_every_handle_size(kd):
     assert all(np.array_equal(x, y[:512]) for x, y in zip(a, c))
 
 
-def test_full_batch_4096_walkers_at_432_sites_matches_oracle_chains(kd):
-    """BASELINE's full single-GPU batch (4096 walkers x 432 sites, device Xoshiro streams, 450 sweeps across the
-    re-evaluations at sweeps 216 and 432): eight walkers picked across the batch (first, last, CTA and list boundaries)
-    must be bit-identical to the oracle's Carlo loop started from the same state -- kappa, acceptance count, O_L sum --
-    and every walker's incremental Z_mu must equal the recount.  (The small replay tests cannot see effects that need a
-    full machine: thousands of (walker, species) items per persistent CTA, hundreds of flushes per launch.)"""
-    lat, ham = U.problem(12, 12)
-    ns, nw, n = kd.ns(lat), 4096, 450
+@pytest.mark.parametrize("n,flux,B,nw,n_sweeps,picks", [
+    (12, "pi", 0.0, 4096, 450, (0, 7, 8, 1023, 2048, 3333, 4094, 4095)),      # headline batch
+    (6, "pi", 0.0, 4096, 500, (0, 443, 444, 2047, 4095)),                     # BASELINE config 2 on k_resident (444 resident CTAs)
+    (6, "zero", 0.0, 4096, 500, (1, 445, 4000)),
+    (12, "pi", 0.02, 4096, 450, (0, 9, 2222, 4095)),                          # ComplexF64 engine, full batch
+    (18, "pi", 0.0, 1024, 500, (0, 511, 1023)),                               # BASELINE config 4: cluster inverse + product
+])
+def test_full_batch_matches_oracle_chains(kd, n, flux, B, nw, n_sweeps, picks):
+    """BASELINE's full single-GPU batches (device Xoshiro streams, sweeps across the periodic re-evaluations): walkers
+    picked across the batch (first, last, CTA / resident-slot / list boundaries) must be bit-identical to the oracle's
+    Carlo loop started from the same state -- kappa, acceptance count, O_L sum, W -- and every walker's incremental
+    Z_mu must equal the recount.  (The small replay tests cannot see effects that need a full machine: thousands of
+    (walker, species) items per persistent CTA, hundreds of flushes per launch, every resident slot taken.)"""
+    lat, ham = U.problem(n, n, (True, True), (True, False), flux, None, B)
+    dtype = "c128" if B != 0.0 else "f64"
+    ns = kd.ns(lat)
     ku0, kd0 = kd.init_conf_qr(ham, ns, ns // 2)
-    states = kd.walker_states(2026, nw)
+    states = kd.walker_states(2026 + n, nw)
     eng = kd.Engine(ham, nw)
+    assert eng.is_complex == (B != 0.0)
     eng.set_config(ku0, kd0)
     eng.set_rng(states)
     eng.refresh()
-    eng.sweep(n, thermalization=100)
+    eng.sweep(n_sweeps, thermalization=100)
     gku, gkd = eng.get_config()
     z, zr = eng.Z()
     assert np.array_equal(z, zr)
     acc, acc_w, ol_w = eng.accumulators(per_walker=True)
     assert acc[kd._lib.ACC_N_SINGULAR] == 0
-    for w in (0, 7, 8, 1023, 2048, 3333, 4094, 4095):
-        mc = U.O.MC(np.asarray(ham.nn, dtype=np.int32), ham.U_up, ham.U_down, "f64")
+    for w in picks:
+        mc = U.O.MC(np.asarray(ham.nn, dtype=np.int32), ham.U_up, ham.U_down, dtype)
         mc.set_kappa(ku0, kd0)
         mc.reevaluateW()
-        st, _ = mc.run(U.O.Xoshiro(states[w]), n, 100)
+        st, _ = mc.run(U.O.Xoshiro(states[w]), n_sweeps, 100)
         oku, okd = mc.kappa()
         assert np.array_equal(gku[w], oku) and np.array_equal(gkd[w], okd), f"walker {w}: configuration differs from the oracle chain"
         assert acc_w[w] == st[0]
