@@ -88,6 +88,7 @@ struct kdsl_handle_s {
     size_t fused_smem24 = 0, fused_smem16 = 0;   // the same for panel widths 24 (default) and 16
     int fused_stage24 = 0, fused_stage16 = 0;
     int fused_ctas = 0;           // resident CTAs of k_reeval_fused (0: one per SM)
+    bool fused_small = false;     // N <= 128, M <= 128, ns <= 256: the 256-thread instantiation, two CTAs per SM
     double *Gbuf = nullptr;       // [nw][2][Gstride] flush operands G = -T Rt in DMMA fragment order (k_flush_G -> k_flush_tma; flush_variant 3 only)
     size_t Gstride = 0;
     size_t res_smem = 0;          // dynamic shared memory of k_resident (0: a walker does not fit one CTA)
@@ -618,7 +619,11 @@ int launch_refresh(kdsl_handle h, const int *list) {
         const size_t fsm = nb32 ? h->fused_smem : v == 5 ? h->fused_smem16 : h->fused_smem24;
         const int fst = nb32 ? h->fused_stage : v == 5 ? h->fused_stage16 : h->fused_stage24;
 #define KDSL_FUSED_LAUNCH(...) k_reeval_fused<__VA_ARGS__><<<fgrid, 512, fsm, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax, fst)
-        if (nb32) {
+        if (h->fused_small && v == 0) {
+            // small lattices: 256-thread CTAs, two per SM (twice the pivot chains in flight)
+            const int sgrid = h->fused_ctas > 0 ? std::min(h->fused_ctas, 2 * h->num_sms) : 2 * h->num_sms;
+            k_reeval_fused<24, 2, 6, 0, 256><<<sgrid, 256, fsm, h->stream>>>(S, list, h->ws_fused, h->ws_stride, h->UT_up, h->UT_dn, h->status, h->Np_up, h->Np_dn, h->fused_NpMax, h->fused_CpMax, fst);
+        } else if (nb32) {
             KDSL_FUSED_LAUNCH(32, 2, 6);
         } else if (v == 1) KDSL_FUSED_LAUNCH(24, 1, 8);
         else if (v == 2) KDSL_FUSED_LAUNCH(24, 2, 4);
@@ -1141,7 +1146,8 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             h->fused_CpMax = CpMax;
             h->ws_stride = std::max((size_t)h->Np_up * (h->Np_up + Mp_up), (size_t)h->Np_dn * (h->Np_dn + Mp_dn));
             ALLOC(h->UT_up, (size_t)(ns + 9) * h->Np_up); ALLOC(h->UT_dn, (size_t)(ns + 9) * h->Np_dn);
-            ALLOC(h->ws_fused, (size_t)h->num_sms * h->ws_stride);
+            h->fused_small = NpMax <= 128 && Mp_up <= 128 && Mp_dn <= 128 && ns <= 256 && 2 * (smem24 + 1024) <= (size_t)prop.sharedMemPerMultiprocessor;
+            ALLOC(h->ws_fused, (size_t)(h->fused_small ? 2 : 1) * h->num_sms * h->ws_stride);
             k_build_UT<<<64, 256, 0, h->stream>>>(dUu, h->UT_up, ns, n_up, h->Np_up);
             k_build_UT<<<64, 256, 0, h->stream>>>(dUd, h->UT_dn, ns, n_dn, h->Np_dn);
             CKD(cudaGetLastError());
@@ -1154,6 +1160,7 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+            if (h->fused_small) CKD(cudaFuncSetAttribute(k_reeval_fused<24, 2, 6, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
             CKD(cudaStreamSynchronize(h->stream));
         }
     }

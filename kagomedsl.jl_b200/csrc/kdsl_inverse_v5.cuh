@@ -20,6 +20,7 @@
 #include "kdsl_refresh_fast.cuh"
 
 __device__ __forceinline__ void bar_team_p() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int TP> __device__ __forceinline__ void bar_team() { asm volatile("bar.sync 1, %0;" ::"n"(TP) : "memory"); }
 
 // 1 / a to about 1 ulp with THREE dependent FP64 instructions after the MUFU seed x0 (relative error e ~ 2^-20 from
 // rcp.approx.ftz.f64):  1/a = x0 (1 + e + e^2 + ...),  x = x0 + x0 (e + e^2), error e^3 ~ 2^-60.  The compiler's IEEE

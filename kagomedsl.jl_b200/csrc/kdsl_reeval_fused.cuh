@@ -162,7 +162,7 @@ struct FusedArgs {
 
 // ---- team P (256 threads, thread j owns row j): factor the panel of columns [k0, k0 + kw); operands R - E -> sM.
 //      Returns true when this thread's row became a pivot in this panel.  FIRST: the columns still live in UT. ----
-template <int NB, bool FIRST>
+template <int NB, bool FIRST, int TP = 256>
 __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double *__restrict__ ws, int k0, int kw,
                                                    double *sM, bool pivoted) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
@@ -245,7 +245,7 @@ __device__ __noinline__ bool fused_factor_panel(const FusedArgs FA, const double
 #pragma unroll
             for (int j = 0; j < NB; j += 2) dst[j >> 1] = make_double2(a[j], a[j + 1]);
         }
-        bar_team_p();
+        bar_team<TP>();
         const int p = sIdx[0];
         const double2 rs = *reinterpret_cast<const double2 *>(sRinv);   // (1 / pivot, pivot row's next entry / pivot)
         if (has_row && tid == p) {
@@ -506,13 +506,13 @@ __device__ __noinline__ void fused_last_step(const FusedArgs FA, const double *_
 
 // ---- phase A: the kn columns of the next panel (from column c0), all 16 warps: item = row tile (at most two per warp,
 //      both loaded up front) ----
-template <int NB, bool FIRST>
+template <int NB, bool FIRST, int NWARPS = 16>
 __device__ __noinline__ void fused_update_next_panel(const FusedArgs FA, double *__restrict__ ws, const double *sM,
                                                         int c0, int kn) {
     const FusedSmem<NB, 16> L(FA.sm, FA.NpMax, FA.CpMax, FA.ns);
     const unsigned long long pol = fused_policy_keep();
     (void)pol;
-    constexpr int KS = NB / 4, NT = NB / 8, NWARPS = 16;
+    constexpr int KS = NB / 4, NT = NB / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gr = lane >> 2, tg = lane & 3;
     const int Np = L.ctx->Np, Cp = L.ctx->Cp;
@@ -622,30 +622,34 @@ __device__ __noinline__ void fused_item_setup(const FusedArgs FA, const DevState
     }
 }
 
-template <int NB, int CT, int DG = 6, int DBG = 0>
-__global__ void __launch_bounds__(512, 1)
+// T = 512 (one CTA per SM; teams of 8 warps; N <= 256, ns <= 512) is the production instantiation; T = 256 (two CTAs per
+// SM; teams of 4 warps; N <= 128, M <= 128, ns <= 256) doubles the matrices in flight on small lattices, where the kernel
+// is bound by the latency of one pivot chain per SM (192 sites: 96 pivots per matrix).
+template <int NB, int CT, int DG = 6, int DBG = 0, int T = 512>
+__global__ void __launch_bounds__(T, T == 512 ? 1 : 2)
 k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws_base, size_t ws_stride,
                const double *__restrict__ UT_up, const double *__restrict__ UT_dn, int *__restrict__ status,
                int Np_up, int Np_dn, int NpMax, int CpMax, int stage_doubles) {
-    constexpr int T = 512, NWARPS = 16, GW = 8;
-    static_assert(NB % 8 == 0, "panel width must be a multiple of 8");
+    constexpr int NWARPS = T / 32, GW = NWARPS / 2, TP = T / 2;
+    static_assert(NB % 8 == 0 && (T == 512 || T == 256), "panel width must be a multiple of 8");
     extern __shared__ double sm[];
     const FusedSmem<NB, NWARPS> L(sm, NpMax, CpMax, S.ns);
     const FusedArgs FA{sm, NpMax, CpMax, S.ns};
     const int n_items = 2 * batch_count(S, list);
     double *ws = ws_base + (size_t)blockIdx.x * ws_stride;
-    if (threadIdx.x == 0) mbar_init((unsigned)__cvta_generic_to_shared(L.sScan + 24), 256);
+    if (threadIdx.x == 0) mbar_init((unsigned)__cvta_generic_to_shared(L.sScan + 24), TP);
+    if (threadIdx.x < 8) L.sKey[threadIdx.x] = 0u;          // (keys of warps that do not exist never win)
     __syncthreads();
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         fused_item_setup<NB, T>(FA, S, list, UT_up, UT_dn, status, Np_up, Np_dn, item);
-        const bool teamP = threadIdx.x < 256;
+        const bool teamP = threadIdx.x < TP;
         bool pivoted = false;                               // my row has been a pivot
         const int Np = L.ctx->Np;
 
         // ---- step 0 panel ----
         const int kw0 = min(NB, Np);
-        if (teamP) pivoted = fused_factor_panel<NB, true>(FA, ws, 0, kw0, L.sMb, pivoted);
+        if (teamP) pivoted = fused_factor_panel<NB, true, TP>(FA, ws, 0, kw0, L.sMb, pivoted);
         __syncthreads();
         if (!L.sIdx[1]) {
             fused_gather_X<NB, T, true>(FA, ws, kw0, kw0);
@@ -659,23 +663,23 @@ k_reeval_fused(DevState S, const int *__restrict__ list, double *__restrict__ ws
                 const double *sM = L.sMb + (size_t)(s & 1) * NB * Np;
                 double *sMn = L.sMb + (size_t)((s + 1) & 1) * NB * Np;
                 const int ntc = L.ctx->Cp >> 3;
-                PHASE_RESTART(256);
+                PHASE_RESTART(TP);
                 FUSED_TICK(4, 0);                           // (loop overhead)
                 if (kn > 0) {
-                    if (first) fused_update_next_panel<NB, true>(FA, ws, sM, k1, kn);
-                    else fused_update_next_panel<NB, false>(FA, ws, sM, k1, kn);
+                    if (first) fused_update_next_panel<NB, true, NWARPS>(FA, ws, sM, k1, kn);
+                    else fused_update_next_panel<NB, false, NWARPS>(FA, ws, sM, k1, kn);
                     __syncthreads();
                     FUSED_TICK(0, 0);
-                    PHASE_RESTART(256);
+                    PHASE_RESTART(TP);
                     if (teamP) {
-                        if (DBG != 2) pivoted = fused_factor_panel<NB, false>(FA, ws, k1, kn, sMn, pivoted);
+                        if (DBG != 2) pivoted = fused_factor_panel<NB, false, TP>(FA, ws, k1, kn, sMn, pivoted);
                         else if (threadIdx.x < kn) { L.sPivRow[threadIdx.x] = k1 + threadIdx.x; L.sStep[k1 + threadIdx.x] = k1 + threadIdx.x; }
                         FUSED_TICK(1, 0);
                     } else if (DBG != 1) {
-                        const int wg = (threadIdx.x >> 5) - 8;
+                        const int wg = (threadIdx.x >> 5) - GW;
                         if (first) fused_update_cols<NB, CT, DG, true>(FA, ws, sM, (k1 + kn) >> 3, ntc, wg, GW, S.ns);
                         else fused_update_cols<NB, CT, DG, false>(FA, ws, sM, (k1 + kn) >> 3, ntc, wg, GW, S.ns);
-                        FUSED_TICK(2, 256);
+                        FUSED_TICK(2, TP);
                     }
                     __syncthreads();
                     FUSED_TICK(5, 0);                       // team P waiting for team G
