@@ -418,6 +418,7 @@ k_unsplit_c(DevState S, const int *__restrict__ list, const double *__restrict__
         }
         __syncthreads();
     }
+    if (!write_X) return;                                 // (k_gemm_W_dmma_c writes the unit rows with its own tiles)
     for (int site = threadIdx.x; site < ns; site += blockDim.x) {
         const int l = kap[site];
         if (l != 0)
@@ -431,7 +432,8 @@ k_unsplit_c(DevState S, const int *__restrict__ list, const double *__restrict__
 // A complex block product is four real DMMAs (the minus sign rides on a negated copy of the Im(U) fragment).
 // CTA = 3 warps, tile 72 sites x 24 columns (warp tile 24 x 24), four CTAs per SM (12 warps = 3 per sub-partition: a 9-warp
 // CTA loses 10-25 % to the 4-way split); register-staged double buffering, fragment-major shared layout.
-// grid (tiles_m * tiles_n, nw, 2).  The unit rows of the occupied sites and the urow lists come from k_unsplit_c.
+// grid (tiles_m * tiles_n, nw, 2).  The urow lists come from k_unsplit_c; the unit rows of the occupied sites are written
+// here, by the CTA whose row tile spans them.
 template <int KT>
 __global__ void __launch_bounds__(96, 4)
 k_gemm_W_dmma_c(DevState S, const int *__restrict__ list, const double *__restrict__ A_up, const double *__restrict__ A_dn,
@@ -442,7 +444,7 @@ k_gemm_W_dmma_c(DevState S, const int *__restrict__ list, const double *__restri
     static_assert(TM * KT % NT == 0 && TN * KT % NT == 0 && KT % 4 == 0, "stage must divide evenly");
     __shared__ double sAr[2][TM * KT], sAi[2][TM * KT], sBr[2][TN * KT], sBi[2][TN * KT];
     __shared__ int sSrc[TN];
-    __shared__ int sRowSite[TM];
+    __shared__ int sRowSite[TM + 1];
     __shared__ int sKp[512 + KT];
     const int b = blockIdx.y, spin = blockIdx.z;
     if (b >= batch_count(S, list)) return;
@@ -462,7 +464,7 @@ k_gemm_W_dmma_c(DevState S, const int *__restrict__ list, const double *__restri
     cplx *W = cW(spin ? S.W_dn : S.W_up, (size_t)w * ns * N);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < TN) sSrc[tid] = (n0 + tid < N) ? colsrc[n0 + tid] : -1;
-    if (tid < TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
+    if (tid <= TM) sRowSite[tid] = (m0 + tid < M) ? urow[m0 + tid] : -1;
     for (int k = tid; k < 512 + KT; k += NT) sKp[k] = k < N ? colsrc[k] : 0;
     __syncthreads();
 
@@ -551,6 +553,19 @@ k_gemm_W_dmma_c(DevState S, const int *__restrict__ list, const double *__restri
                 const int site = sRowSite[24 * warp + 8 * i + gr];
                 if (site >= 0) W[(size_t)n * ns + site] = c_make(cr[i][j][e], ci[i][j][e]);
             }
+        }
+    }
+    // unit rows of the occupied sites inside this tile's site range [s_lo, s_hi), for this CTA's 24 columns: together with
+    // the stores above every 32-byte sector of the range is completed by this CTA
+    const int *kap = (spin ? S.kdn : S.kup) + (size_t)w * ns;
+    const int s_lo = (tm == 0) ? 0 : sRowSite[0];
+    const int s_hi = (tm == tiles_m - 1 || sRowSite[TM] < 0) ? ns : sRowSite[TM];
+    const int ncols = min(TN, N - n0);
+    for (int site = s_lo + tid; site < s_hi; site += NT) {
+        const int l = kap[site];
+        if (l != 0) {
+            cplx *dst = W + (size_t)n0 * ns + site;
+            for (int cc = 0; cc < ncols; cc++) dst[(size_t)cc * ns] = c_make((l - 1 == n0 + cc) ? 1.0 : 0.0, 0.0);
         }
     }
 }
