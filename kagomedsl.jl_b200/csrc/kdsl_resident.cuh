@@ -248,8 +248,19 @@ __device__ __forceinline__ bool res_reevaluate(const DevState &S, const ResSmem 
                 f[r] = pt[r][0];
 #pragma unroll
                 for (int t = 0; t < NP; t++) {
+                    // The loads are NOT predicated on the column masks of the stores: a lane past the row end reads entries
+                    // of the next row (inside the allocation) that are never used -- neither stored nor fed into a stored
+                    // value.  Their owner warp may update them at the same time, which compute-sanitizer racecheck reports as
+                    // a read-write hazard; it is benign, and predicating the loads costs 9 % of the kernel (146 -> 132.5 M
+                    // walker-sweeps/s at 108 sites: two more instructions per load in an issue-bound loop).  `make STRICT=1`
+                    // builds the predicated form, on which racecheck is clean (profiles/r4_sanitizer.txt).
+#ifdef KDSL_STRICT_LOADS
+                    if (t == 0 || (t == 1 ? t1T : k + 1 + 32 * t < N)) vT[r][t] = cT[t] ? pt[r][1 + lane + 32 * t] : 0.0;
+                    vV[r][t] = cV[t] ? pw[r][32 * t] : 0.0;
+#else
                     if (t == 0 || (t == 1 ? t1T : k + 1 + 32 * t < N)) vT[r][t] = pt[r][1 + lane + 32 * t];
                     vV[r][t] = pw[r][32 * t];
+#endif
                 }
             }
 #pragma unroll
