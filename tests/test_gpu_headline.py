@@ -376,6 +376,53 @@ def test_energy_432_sites_within_error_bars(kd):
     assert abs(e_gpu - e_cpu) < 4.0 * np.hypot(s_gpu, s_cpu), (e_gpu, s_gpu, e_cpu, s_cpu)
 
 
+def test_energy_c128_landau_level_192_sites_within_error_bars(kd):
+    """The same statistical check for the ComplexF64 engine: scripts/LL.jl's 8x8 lattice (192 sites, antiPBC = (false, true),
+    Peierls flux with imbalance 2, N_up = 97, N_down = 95).  GPU: 2048 walkers x 40 bins on the complex tensor-pipe kernels;
+    oracle (c128 instantiation): one walker per host core x 600 bins, run here.  |dE| < 4 sigma."""
+    n1 = n2 = 8
+    B = 2 * np.pi / (n1 * n2 * 2 * np.sqrt(3.0))
+    lat, ham = U.problem(n1, n2, (True, True), (False, True), "pi", 97, B)
+    ns = kd.ns(lat)
+    n_occ = min(ham.N_up, ham.N_down)
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ham.N_up)
+    nw, bins_gpu, therm = 2048, 40, 40 * n_occ
+    eng = kd.Engine(ham, nw)
+    assert eng.is_complex
+    eng.set_config(ku0, kd0)
+    eng.set_rng(kd.walker_states(4321, nw))
+    eng.refresh()
+    eng.sweep(therm, -1)
+    eng.reset_accumulators()
+    eng.sweep(bins_gpu * n_occ, 0)
+    acc, acc_w, ol_w = eng.accumulators(per_walker=True)
+    eng.close()
+    assert acc[kd._lib.ACC_N_SINGULAR] == 0 and acc[kd._lib.ACC_N_OL] == nw * bins_gpu
+    e_w = ol_w / bins_gpu / ns
+    e_gpu, s_gpu = e_w.mean(), e_w.std(ddof=1) / np.sqrt(nw)
+    cores = min(os.cpu_count() or 1, 32)
+    bins_cpu = 600
+    bonds = np.asarray(ham.nn, dtype=np.int32)
+    res = [None] * cores
+
+    def work(t):
+        mc = U.O.MC(bonds, ham.U_up, ham.U_down, "c128")
+        mc.set_kappa(ku0, kd0)
+        mc.reevaluateW()
+        g = U.O.Xoshiro.from_seed(77 + 7919 * t)
+        mc.run(g, therm, 10 ** 12)
+        st = np.zeros(4)
+        mc.run(g, bins_cpu * n_occ, 0, stats=st)
+        res[t] = st
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
+    [th.start() for th in ths]
+    [th.join() for th in ths]
+    e_c = np.array([r_[1] / r_[3] / ns for r_ in res])
+    e_cpu, s_cpu = e_c.mean(), e_c.std(ddof=1) / np.sqrt(cores)
+    print("E/site c128 192 sites: GPU %.6f +- %.6f, oracle chain %.6f +- %.6f" % (e_gpu, s_gpu, e_cpu, s_cpu))
+    assert s_gpu < 2e-4 and abs(e_gpu - e_cpu) < 4.0 * np.hypot(s_gpu, s_cpu), (e_gpu, s_gpu, e_cpu, s_cpu)
+
+
 def test_two_gpus_reduce_accumulators_through_the_c_abi(kd):
     """kdsl_comm_init_all + kdsl_group_accumulators_allreduce: one process, one handle per GPU (the Julia host's layout);
     the NCCL sum equals the sum of the per-handle vectors.  Needs two visible GPUs (gpurun --gpus 2)."""
