@@ -760,7 +760,7 @@ int launch_flush(kdsl_handle h, bool all) {
             Span sp(h, KDSL_T_UPDATE);
             if (h->flush_variant == 0 && h->fdc_RB > 0) {     // tensor-pipe flush (k_flush_dmma_c), one persistent CTA per SM
                 const int Npad = (Np + 7) / 8 * 8;
-                k_flush_dmma_c<24, 3><<<h->num_sms, 512, flush_dmma_c_smem(24, Npad, h->fdc_RB), h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Npad, h->fdc_RB);
+                k_flush_dmma_c<24, 4><<<h->num_sms, 512, flush_dmma_c_smem(24, Npad, h->fdc_RB), h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Npad, h->fdc_RB);
             } else {
                 k_flush_c<24, 216><<<h->num_sms * per_sm, 224, smem, h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Np);
             }
@@ -1210,14 +1210,14 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
                                  (int)((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
         {
             // k_flush_dmma_c: the fewest row blocks per species whose operands fit the shared memory
-            CKD(cudaFuncGetAttributes(&fa, (const void *)k_flush_dmma_c<24, 3>));
+            CKD(cudaFuncGetAttributes(&fa, (const void *)k_flush_dmma_c<24, 4>));
             const size_t lim = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
             const int Npad = (std::max(n_up, n_dn) + 7) / 8 * 8;
             for (int nrb = 1; nrb <= 64 && !h->fdc_RB; nrb++) {
                 const int RB = (((int)ns + nrb - 1) / nrb + 7) / 8 * 8;
                 if (flush_dmma_c_smem(24, Npad, RB) <= lim) h->fdc_RB = RB;
             }
-            if (h->fdc_RB) CKD(cudaFuncSetAttribute(k_flush_dmma_c<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_dmma_c_smem(24, Npad, h->fdc_RB)));
+            if (h->fdc_RB) CKD(cudaFuncSetAttribute(k_flush_dmma_c<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_dmma_c_smem(24, Npad, h->fdc_RB)));
         }
         const size_t need_f = (size_t)24 * std::max(n_up, n_dn) * 2 * sizeof(double);
         if (measure_wb_smem_c(S) > h->smem_optin || need_f + fa.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) {
