@@ -59,7 +59,7 @@ def main():
              "invclc": ("k_inverse_cl_c_dram_bytes_per_walker_refresh", 4096), "gemmc": ("k_gemm_W_dmma_c_dram_bytes_per_walker_refresh", 4096),
              "invcl972": ("k_inverse_cl_dram_bytes_per_matrix_972", 1024)}
     for name in ("fused", "inverse", "gemm", "flush", "decide", "measure", "gather", "resident", "inverse972", "gemm972", "flush972", "flushc",
-                 "invclc", "gemmc", "flushdc", "invcl972"):
+                 "invclc", "gemmc", "flushdc", "invcl972", "fused192"):
         rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (name, TAG))
         if not os.path.exists(rep):
             print("missing", rep)
