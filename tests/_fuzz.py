@@ -40,6 +40,18 @@ def run_fuzz(seed, budget_s):
         states = kd.walker_states(int(rng.integers(1, 10 ** 6)), nw)
         dtype = "c128" if B != 0.0 else "f64"
         eng = kd.Engine(ham, nw)
+        # the default path of this size, or one of the other selectable paths (lock-step Woodbury / rank-1 updates, the
+        # three-kernel re-evaluation; ComplexF64: embedding inverse, FMA flush and product)
+        opts = [{}, {}, {"update_variant": 2}, {"update_variant": 0}, {"update_variant": 2, "inverse_variant": 5}]
+        if B != 0.0:
+            opts = [{}, {}, {"update_variant": 0}, {"inverse_variant": 7, "flush_variant": 4, "gemm_variant": 4}]
+        opt = opts[int(rng.integers(0, len(opts)))]
+        try:
+            for k_, v_ in opt.items():
+                eng.set_option(k_, v_)
+        except kd.KdslError:
+            pass
+        desc += f" opts={opt}"
         eng.set_config(ku0, kd0)
         eng.set_rng(states)
         try:
