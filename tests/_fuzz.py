@@ -8,12 +8,12 @@ import kagomedsl.jl_b200 as kd
 from oracle import oracle as O
 
 
-def run_fuzz(seed, budget_s):
+def run_fuzz(seed, budget_s, big=False):
     rng = np.random.default_rng(seed)
     t0 = time.time()
     n_ok = n_skip = 0
     while time.time() - t0 < budget_s:
-        n1 = int(rng.choice([2, 4, 6, 8])); n2 = int(rng.integers(2, 9))
+        n1 = int(rng.choice([2, 4, 6, 8, 10, 12] if big else [2, 4, 6, 8])); n2 = int(rng.integers(2, 13 if big else 9))
         PBC = (bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
         anti = (bool(rng.integers(0, 2)) and PBC[0], bool(rng.integers(0, 2)) and PBC[1])
         flux = str(rng.choice(["pi", "zero"]))
