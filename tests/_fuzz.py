@@ -56,7 +56,11 @@ def run_fuzz(seed, budget_s, big=False):
         eng.set_rng(states)
         try:
             eng.refresh()
-            eng.sweep(n, thermalization=therm)
+            cuts = sorted(set(int(c) for c in rng.integers(1, n, size=int(rng.integers(0, 3)))))   # 1..3 calls: the chain must not care
+            done = 0
+            for c in cuts + [n]:
+                eng.sweep(c - done, thermalization=therm)
+                done = c
             gku, gkd = eng.get_config()
             z, zr = eng.Z()
             acc, acc_w, ol_w = eng.accumulators(per_walker=True)
