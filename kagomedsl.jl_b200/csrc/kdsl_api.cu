@@ -136,6 +136,7 @@ struct kdsl_handle_s {
     double *clc_scratch = nullptr;
     int clc_scratch_clusters = 0;
     int fdc_RB = 0;               // rows per item of k_flush_dmma_c (0: it does not fit, k_flush_c runs)
+    int fd2_RB = 0;               // rows per item of k_flush_dmma2_c (two CTAs per SM; 0: it does not fit)
     int reeval_rs = 4;            // row slices per column-tile pair of its trailing update
     int update_ch = 8;
     // profiling
@@ -758,7 +759,9 @@ int launch_flush(kdsl_handle h, bool all) {
         const int per_sm = 2 * (smem + 12 * 1024) <= (size_t)227 * 1024 ? 2 : 1;
         {
             Span sp(h, KDSL_T_UPDATE);
-            if (h->flush_variant == 0 && h->fdc_RB > 0) {     // tensor-pipe flush (k_flush_dmma_c), one persistent CTA per SM
+            if (h->flush_variant == 0 && h->fd2_RB > 0) {     // tensor-pipe flush, two persistent 256-thread CTAs per SM
+                k_flush_dmma2_c<24, 4><<<2 * h->num_sms, 256, flush_dmma2_c_smem(24, h->fd2_RB), h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, h->fd2_RB);
+            } else if ((h->flush_variant == 0 || h->flush_variant == 7) && h->fdc_RB > 0) {     // k_flush_dmma_c, one persistent CTA per SM
                 const int Npad = (Np + 7) / 8 * 8;
                 k_flush_dmma_c<24, 4><<<h->num_sms, 512, flush_dmma_c_smem(24, Npad, h->fdc_RB), h->stream>>>(S, list, cptr, S.nw, S.cnt + 5, Npad, h->fdc_RB);
             } else {
@@ -1218,6 +1221,12 @@ static int create_impl(kdsl_handle *out, int device, int ns, int n_up, int n_dn,
                 if (flush_dmma_c_smem(24, Npad, RB) <= lim) h->fdc_RB = RB;
             }
             if (h->fdc_RB) CKD(cudaFuncSetAttribute(k_flush_dmma_c<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_dmma_c_smem(24, Npad, h->fdc_RB)));
+            // k_flush_dmma2_c: two CTAs per SM -- the C planes of a row block and T must fit half an SM
+            for (int nrb = 1; nrb <= 64 && !h->fd2_RB; nrb++) {
+                const int RB = (((int)ns + nrb - 1) / nrb + 7) / 8 * 8;
+                if (2 * (flush_dmma2_c_smem(24, RB) + 2048) <= (size_t)prop.sharedMemPerMultiprocessor) h->fd2_RB = RB;
+            }
+            if (h->fd2_RB) CKD(cudaFuncSetAttribute(k_flush_dmma2_c<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flush_dmma2_c_smem(24, h->fd2_RB)));
         }
         const size_t need_f = (size_t)24 * std::max(n_up, n_dn) * 2 * sizeof(double);
         if (measure_wb_smem_c(S) > h->smem_optin || need_f + fa.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) {
@@ -1685,7 +1694,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
     if (h && h->cplx && name) {
         const std::string nm(name);
         if ((nm == "update_variant" && value != 0 && value != 2) || (nm == "inverse_variant" && value != 0 && value != 1 && value != 4 && value != 5 && value != 7 && value != 9) ||
-            (nm == "flush_variant" && value != 0 && value != 4))
+            (nm == "flush_variant" && value != 0 && value != 4 && value != 7))
             return fail(KDSL_ERR_STATE, "option %s = %lld is not available in ComplexF64 mode (update_variant 0 / 2; flush_variant 0 = tensor-pipe flush, 4 = FMA flush; inverse_variant 0 / 9 = complex cluster inverse, 4 / 5 / 7 = blocked inverse of the real embedding, 1 = unblocked complex)", name, (long long)value);
         if (nm == "update_variant" && value == 2 && measure_wb_smem_c(h->S) > h->smem_optin)
             return fail(KDSL_ERR_INVALID_ARGUMENT, "the ComplexF64 Woodbury kernels need %zu bytes of shared memory at ns = %d (device limit %zu)",
@@ -1743,7 +1752,7 @@ int kdsl_set_option(kdsl_handle h, const char *name, int64_t value) {
             if (rc) return rc;
             if ((rc = dev_alloc(h, &h->Gbuf, (size_t)2 * h->S.nw * h->Gstride))) return rc;
         }
-        if (value != 0 && value != 3 && !(h->cplx && value == 4)) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
+        if (value != 0 && value != 3 && !(h->cplx && (value == 4 || value == 7))) return fail(KDSL_ERR_INVALID_ARGUMENT, "flush_variant %lld is a developer variant (build with make DEV=1)", (long long)value);
 #endif
         h->flush_variant = (int)value;
     }

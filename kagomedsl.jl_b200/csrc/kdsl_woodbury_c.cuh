@@ -490,6 +490,155 @@ k_flush_dmma_c(DevState S, const int *__restrict__ list, const int *__restrict__
         }
     }
 }
+// k_flush_dmma2_c: the same pass with TWO 256-thread CTAs per SM.  k_flush_dmma_c keeps G = -T Rt of the whole species in shared
+// memory (83 KB at 432 sites), which leaves room for one CTA per SM -- and nothing streams while that CTA runs an item's prologue.
+// Here a warp builds the G fragments of ITS column tile itself, on the tensor pipe, right before it streams the tile:
+//   G^T[j][m] = -sum_n Rt[n][j] T[m][n]:  A operand = Rt^T (8 columns j x 24 n, read from the row copies), B operand = T^T (shared
+//   memory, fragment order), 72 real DMMAs per column tile (11 % of the tile's 648); the accumulator fragment (j, m = 2t, 2t + 1) is
+//   turned into the A-operand fragment (j, m = 4 ks + t) of the streaming loop by two quad shuffles per value.
+// Shared memory: C planes [RB x KP] x 2 + T^T planes [KP x KP] x 2 = 92 KB at 432 sites -> two CTAs per SM cover each other's prologues.
+template <int KP, int D>
+__global__ void __launch_bounds__(256, 2)
+k_flush_dmma2_c(DevState S, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
+                int *__restrict__ work_counter, int RB) {
+    constexpr int KS = KP / 4, MT = KP / 8, T_ = 256, NWARPS = 8;
+    static_assert(KP % 8 == 0, "pending-update capacity must be a multiple of 8");
+    extern __shared__ __align__(16) unsigned char fd2sm[];
+    double *sCr = reinterpret_cast<double *>(fd2sm);      // [RB x KP] frag-major (r = row, k = m): Re W0[row, l_m]
+    double *sCi = sCr + (size_t)RB * KP;
+    double *sTr = sCi + (size_t)RB * KP;                  // [KP x KP] frag-major (r = m, k = n): Re T[m][n] (B operand: k = n, col = m)
+    double *sTi = sTr + KP * KP;
+    int *sL = reinterpret_cast<int *>(sTi + KP * KP);
+    __shared__ int s_item;
+    const int count = count_ptr ? *count_ptr : count_fixed;
+    const int ns = S.ns;
+    const int nrb = (ns + RB - 1) / RB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gr = lane >> 2, tg = lane & 3;
+    const int total = count * 2 * nrb;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int e = item / (2 * nrb);
+        const int rem = item - e * 2 * nrb;
+        const int spin = rem / nrb, rb = rem - spin * nrb;
+        const int w = list ? list[e] : e;
+        const WbViewC v = wb_view_c(S, w, spin);
+        const int cnt = v.k;
+        if (cnt == 0) continue;                           // uniform over the block
+        const int N = v.N;
+        const int nks = (cnt + 3) >> 2;                   // k-steps that hold pending updates
+        double *W0 = reinterpret_cast<double *>(const_cast<cplx *>(v.W0));
+        for (int x = tid; x < KP * KP; x += T_) {
+            const int m = x / KP, n = x - m * KP;
+            const cplx t = (m < cnt && n < cnt) ? v.T[m * S.kmax + n] : c_make(0.0, 0.0);
+            const int fi = frag_idx(m, n, KP);
+            sTr[fi] = t.x;
+            sTi[fi] = t.y;
+        }
+        if (tid < KP) sL[tid] = tid < cnt ? v.Ls[tid] : -1;
+        __syncthreads();
+        // C[row][m] = W0[row, l_m] for the rows of this block (all of them read before any store of this item)
+        const int r0 = rb * RB, nrows = min(RB, ns - r0);
+        const int nrt = (nrows + 7) >> 3;
+        for (int idx = tid; idx < (nrt << 3) * (4 * nks); idx += T_) {
+            const int m = idx / (nrt << 3), r = idx - m * (nrt << 3);
+            cplx c = c_make(0.0, 0.0);
+            if (m < cnt && r < nrows) c = v.W0[(size_t)sL[m] * ns + r0 + r];
+            const int fi = frag_idx(r, m, KP);
+            sCr[fi] = c.x;
+            sCi[fi] = c.y;
+        }
+        __syncthreads();
+        const int njt = (N + 7) >> 3;
+        for (int jt = warp; jt < njt; jt += NWARPS) {
+            const int j = (jt << 3) + gr;
+            const bool jok = j < N;
+            // ---- G^T fragments of this column tile: D[j][m] = sum_n Rt[n][j] T[m][n] (complex), then negated ----
+            double dr[MT][2], di[MT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) dr[mt][0] = dr[mt][1] = di[mt][0] = di[mt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                if (ks < nks) {
+                    const int n = 4 * ks + tg;
+                    cplx rt = (jok && n < cnt) ? v.rows[(size_t)n * N + j] : c_make(0.0, 0.0);
+                    if (n < cnt && sL[n] == j) rt.x -= 1.0;
+                    const double an = -rt.y;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double br = sTr[(((mt * KS) + ks) << 5) + lane], bi = sTi[(((mt * KS) + ks) << 5) + lane];
+                        dmma_8x8x4(dr[mt][0], dr[mt][1], rt.x, br);
+                        dmma_8x8x4(di[mt][0], di[mt][1], rt.x, bi);
+                        dmma_8x8x4(dr[mt][0], dr[mt][1], an, bi);
+                        dmma_8x8x4(di[mt][0], di[mt][1], rt.y, br);
+                    }
+                }
+            }
+            // accumulator fragment (j, m = 8 mt + 2 t, + 1)  ->  A-operand fragment (j, m = 4 ks + t), G = -D
+            double g_r[KS], g_i[KS], g_n[KS];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {             // ks = 2 mt + h: m = 8 mt + 4 h + t lives in lane 2 h + (t >> 1), slot t & 1
+                    const int src = (lane & ~3) | (2 * h + (tg >> 1));
+                    const double r0v = __shfl_sync(0xffffffffu, dr[mt][0], src), r1v = __shfl_sync(0xffffffffu, dr[mt][1], src);
+                    const double i0v = __shfl_sync(0xffffffffu, di[mt][0], src), i1v = __shfl_sync(0xffffffffu, di[mt][1], src);
+                    g_r[2 * mt + h] = -((tg & 1) ? r1v : r0v);
+                    g_i[2 * mt + h] = -((tg & 1) ? i1v : i0v);
+                    g_n[2 * mt + h] = -g_i[2 * mt + h];
+                }
+            }
+            // ---- stream the column tile down the block's row tiles ----
+            double *base = W0 + 2 * ((size_t)j * ns + r0 + 2 * tg);
+            double2 b0[D], b1[D];
+            auto ld = [&](int rt, double2 &x0, double2 &x1) {
+                const int rl = min(rt, nrt - 1);
+                const int row = (rl << 3) + 2 * tg;
+                const double2 *p = reinterpret_cast<const double2 *>(base + 16 * rl);
+                x0 = (jok && row < nrows) ? __ldcs(p) : make_double2(0.0, 0.0);
+                x1 = (jok && row + 1 < nrows) ? __ldcs(p + 1) : make_double2(0.0, 0.0);
+            };
+            auto tile = [&](int rt, double2 &x0, double2 &x1) {
+                double2 cr = make_double2(x0.x, x1.x), ci = make_double2(x0.y, x1.y);
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    if (ks < nks) {
+                        const double br = sCr[(((rt * KS) + ks) << 5) + lane], bi = sCi[(((rt * KS) + ks) << 5) + lane];
+                        dmma_8x8x4(cr.x, cr.y, g_r[ks], br);
+                        dmma_8x8x4(ci.x, ci.y, g_r[ks], bi);
+                        dmma_8x8x4(cr.x, cr.y, g_n[ks], bi);
+                        dmma_8x8x4(ci.x, ci.y, g_i[ks], br);
+                    }
+                }
+                const int row = (rt << 3) + 2 * tg;
+                double2 *p = reinterpret_cast<double2 *>(base + 16 * rt);
+                if (jok && row < nrows) __stcs(p, make_double2(cr.x, ci.x));
+                if (jok && row + 1 < nrows) __stcs(p + 1, make_double2(cr.y, ci.y));
+            };
+#pragma unroll
+            for (int i = 0; i < D; i++) ld(i, b0[i], b1[i]);
+            int rt0 = 0;
+#pragma unroll 1
+            for (; rt0 + D <= nrt; rt0 += D) {
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    tile(rt0 + i, b0[i], b1[i]);
+                    ld(rt0 + i + D, b0[i], b1[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D - 1; i++)
+                if (rt0 + i < nrt) tile(rt0 + i, b0[i], b1[i]);
+        }
+    }
+}
+inline size_t flush_dmma2_c_smem(int KP, int RB) {
+    return ((size_t)2 * RB * KP + (size_t)2 * KP * KP) * sizeof(double) + (size_t)KP * sizeof(int);
+}
 inline size_t flush_dmma_c_smem(int KP, int Npad, int RB) {
     return ((size_t)2 * Npad * KP + (size_t)2 * RB * KP + (size_t)2 * KP * KP) * sizeof(double) + (size_t)KP * sizeof(int);
 }

@@ -639,11 +639,11 @@ def test_complex_cluster_inverse_singular_matrix_is_flagged(kd):
     eng.close()
 
 
-@pytest.mark.parametrize("variant,flush", [(2, 0), (2, 4), (0, 0)])
+@pytest.mark.parametrize("variant,flush", [(2, 0), (2, 7), (2, 4), (0, 0)])
 def test_complex_replay_and_device_rng_match_oracle(kd, variant, flush):
     """ComplexF64 chain: replayed proposals -> kappa / Z_mu / counters bit-exact, W within 1e-10; device Xoshiro ->
     same trajectory, counters and O_L sums as the oracle's Carlo loop.  variant 2 = Woodbury delayed updates (default;
-    flush 0 = tensor-pipe flush k_flush_dmma_c, 4 = FMA flush k_flush_c), 0 = the reference's immediate rank-1 update."""
+    flush 0 = tensor-pipe flush k_flush_dmma2_c with two CTAs per SM, 7 = k_flush_dmma_c with one, 4 = FMA flush k_flush_c), 0 = the reference's immediate rank-1 update."""
     lat, ham = _complex_problem(kd, 4, 3, 0.37)
     ns, nw, n_sweeps = kd.ns(lat), 6, 900
     rng = np.random.default_rng(8)
