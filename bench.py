@@ -360,7 +360,7 @@ def run_ours(args):
     # per ACCEPTED move.
     if woodbury:
         n_units, unit_name = upd["flushes"], "walker flush"
-        kname = ("k_flush_dmma_c (delayed rank-k update of the ComplexF64 W: four real DMMAs per complex block product, 128-bit streaming)" if cplx else
+        kname = ("k_flush_dmma2_c (delayed rank-k update of the ComplexF64 W: four real DMMAs per complex block product, two CTAs per SM, 128-bit streaming)" if cplx else
                  "k_flush_wb (delayed rank-k Sherman-Morrison update of W, DMMA, 128-bit streaming)")
         n_launch = max(upd["launches"] // 2, 1)
     else:
