@@ -4,10 +4,11 @@
 // all products bilinear (update_W! is an unconjugated geru, src/MonteCarlo.jl:279-292), the acceptance uses
 // abs2(ratio) (:581) and O_L is real(OL) (src/Hamiltonian.jl:777).  Matrix elements are interleaved (re, im) doubles.
 //   k_decide_wb_c   proposals of up to 8 consecutive sweeps per launch, one warp per walker
-//   k_flush_c       W0 += C G (G = -T Rt) for the listed walkers: one thread per row, the row's k entries of C in
-//                   registers, G broadcast from shared memory, complex FMAs on the FP64 pipe (4 k real FMAs per 32 bytes
-//                   moved: about as much arithmetic time as HBM time, no tensor form needed to leave the rank-1 path,
-//                   whose 32 ns^2 bytes per ACCEPTED move were 52 % of the ComplexF64 step, far behind)
+//   k_flush_dmma2_c W0 += C G (G = -T Rt) for the listed walkers on the FP64 tensor pipe, four real DMMAs per complex block
+//                   product on split (re, im) fragment planes, two 256-thread CTAs per SM (production);
+//   k_flush_dmma_c  the same with G of the whole species in shared memory and one 512-thread CTA per SM (flush_variant 7, and
+//                   the fall-back when two CTAs do not fit);  k_flush_c: the FMA-pipe version, one thread per row (flush_variant 4,
+//                   and the fall-back for sizes whose operands do not fit the shared memory)
 //   k_measure_wb_c  O_L with Woodbury-form entries
 // The real path's k_flush_finish_wb and refresh status kernels are shared (they only touch counters).
 #pragma once
