@@ -423,6 +423,37 @@ def test_energy_c128_landau_level_192_sites_within_error_bars(kd):
     assert s_gpu < 2e-4 and abs(e_gpu - e_cpu) < 4.0 * np.hypot(s_gpu, s_cpu), (e_gpu, s_gpu, e_cpu, s_cpu)
 
 
+def test_two_host_threads_drive_two_handles_concurrently(kd):
+    """One handle per host thread (SURVEY 8(b) threading): two threads sweep their own handles on the same GPU at the same
+    time (ctypes releases the GIL, the kernels of the two streams interleave); each must end exactly where it ends alone."""
+    lat, ham = U.problem(8, 8)
+    ns, nw, n = kd.ns(lat), 256, 400
+    ku0, kd0 = kd.init_conf_qr(ham, ns, ns // 2)
+
+    def run(first, out, k):
+        eng = kd.Engine(ham, nw)
+        eng.set_config(ku0, kd0)
+        eng.set_rng(kd.walker_states(99, nw, first_walker=first))
+        eng.refresh()
+        for _ in range(4):
+            eng.sweep(n // 4, thermalization=50)
+        out[k] = (eng.get_config(), eng.accumulators(per_walker=True), eng.get_rng())
+        eng.close()
+
+    alone = {}
+    run(0, alone, 0)
+    run(nw, alone, 1)
+    both = {}
+    ths = [threading.Thread(target=run, args=(k * nw, both, k)) for k in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for k in range(2):
+        (ku_a, kd_a), (acc_a, accw_a, ol_a), rng_a = alone[k]
+        (ku_b, kd_b), (acc_b, accw_b, ol_b), rng_b = both[k]
+        assert np.array_equal(ku_a, ku_b) and np.array_equal(kd_a, kd_b) and np.array_equal(rng_a, rng_b)
+        assert np.array_equal(accw_a, accw_b) and np.array_equal(ol_a, ol_b) and np.array_equal(acc_a, acc_b)
+
+
 def test_two_gpus_reduce_accumulators_through_the_c_abi(kd):
     """kdsl_comm_init_all + kdsl_group_accumulators_allreduce: one process, one handle per GPU (the Julia host's layout);
     the NCCL sum equals the sum of the per-handle vectors.  Needs two visible GPUs (gpurun --gpus 2)."""
