@@ -333,6 +333,9 @@ def test_error_paths(kd):
         eng.sweep(1)                                    # W stale
     eng.refresh()
     eng.sweep(10)
+    for name, value in (("inverse_variant", 9), ("flush_variant", 4), ("flush_variant", 7), ("inverse_variant", 12), ("no_such_option", 1)):
+        with pytest.raises(kd.KdslError):
+            eng.set_option(name, value)                 # ComplexF64-only variants / unknown names are rejected on the real engine
     eng.close()
     # rank-deficient orbitals -> SingularException (reference: test-MonteCarlo.jl:429-477)
     Ud = np.zeros((12, 6)); Ud[:6] = np.eye(6)
