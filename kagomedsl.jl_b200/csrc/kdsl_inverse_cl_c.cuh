@@ -239,8 +239,12 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
         };
 
         // ---- panel 0 ----
+        long long t_phase = PHASE_CLOCK();                  // (developer phase clocks: make TICKS=1, tools/clc_phases.py)
         if (isP) factor_panel(0, min(NB, Np), 0);
+        CL_TICK(0, 1);
         cl_sync();
+        CL_TICK(0, 2);
+        CL_TICK(1, 6);
         bool sing = false;
         for (int k0 = 0, s = 0; k0 < Np; k0 += NB, s++) {
             const int *Pgs = Pg + (s & 1) * KDSL_CL_PGS;
@@ -280,7 +284,9 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
                         }
                     }
                     __syncthreads();
+                    CL_TICK(0, 0);
                     factor_panel(k1, kn, (s + 1) & 1);
+                    CL_TICK(0, 1);
                 }
             } else {
                 // operands and pivot rows of step s: scratch -> shared memory (re and im planes are adjacent in both)
@@ -292,6 +298,7 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
                     if (tid < NB) sPivRow[tid] = __ldcg(Pgs + tid);
                 }
                 __syncthreads();
+                CL_TICK(1, 3);
                 // my column-tile groups: g = grank, grank + NG, ... over the tiles outside [ex0, ex0 + exn)
                 const int nct = nrt - exn;
                 const int groups = (nct + CT - 1) / CT;
@@ -302,6 +309,7 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
                     return (t / CT) % NG == grank;
                 });
                 __syncthreads();
+                CL_TICK(1, 4);
                 const int n_my = groups > grank ? (groups - grank + NG - 1) / NG : 0;
                 const int items = n_my * RS;
                 for (int it = warp; it < items; it += NWARPS) {
@@ -358,8 +366,14 @@ k_inverse_cl_c(DevState S, const int *__restrict__ list, double *__restrict__ A_
                     }
                 }
             }
+            CL_TICK(1, 5);
             cl_sync();
+            CL_TICK(0, 2);
+            CL_TICK(1, 6);
         }
+#ifdef KDSL_PHASE_TICKS
+        if (blockIdx.x == 0 && tid == 0) g_inv_phase_cycles[15] += 1;
+#endif
         if (sing) cl_sync();                            // nobody re-reads the flag after P has moved on to the next item
         // ---- index map for the consumer: colsrc[i] = elimination step at which row i was the pivot ----
         if (has_row && !sing) colsrc_base[((size_t)2 * b + spin) * cs_stride + tid] = gstep;
